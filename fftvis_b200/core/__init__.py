@@ -1,0 +1,2 @@
+"""Host-side (numpy) planners of the fftvis hot path; see SURVEY.md section 8."""
+from . import antenna_gridding, catalog, coords, utils  # noqa: F401
