@@ -1,0 +1,26 @@
+// Library-wide state of the C ABI: error string, launch counter, version.
+#include "common.cuh"
+
+namespace fv {
+static thread_local std::string g_error;
+int64_t g_launches = 0;
+void set_error(const std::string& msg) { g_error = msg; }
+}  // namespace fv
+
+extern "C" const char* fv_last_error_string(void) { return fv::g_error.c_str(); }
+extern "C" int fv_version(void) { return 100; }
+extern "C" int64_t fv_launch_count(void) { return fv::g_launches; }
+
+extern "C" int fv_device_count(int* count_host) {
+  FV_REQUIRE(count_host, "null pointer");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    *count_host = 0;
+    fv::set_error("no CUDA device: fftvis_b200 has no CPU fallback");
+    return FV_ERR_NO_DEVICE;
+  }
+  *count_host = n;
+  return FV_OK;
+}

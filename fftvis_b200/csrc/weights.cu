@@ -1,0 +1,256 @@
+// Stages a4 + a5 of the hot path fused: per-frequency beam evaluation (analytic or az/za table
+// interpolation) and the apparent-coherency product, emitting the NUFFT strengths directly.
+// Replaces: CPUBeamEvaluator.evaluate_beam (reference cpu/beams.py:12-89; pyuvdata compute_response),
+//   _evaluate_beam_list (cpu_simulate.py:38-87), _compute_apparent_coherency (cpu_simulate.py:90-202)
+//   and the four numba kernels (cpu/beams.py:129-246).
+// One thread per (source, frequency); beam arithmetic in fp64 (the reference evaluates beams in
+// fp64 and casts, cpu_simulate.py:84-86), products in the working precision.  Catalogue fluxes are
+// stored frequency-major so that the gather through src_idx (ascending) is coalesced.
+#include "common.cuh"
+
+namespace fv {
+
+constexpr double kC = 299792458.0;
+
+struct BeamVal { double re[4], im[4]; };   // efield: [vec*2+feed]; power: re[0]
+
+template <typename T> struct tab_elem;      // how table entries are stored
+template <> struct tab_elem<float> { using real = float; using cplx = float2; };
+template <> struct tab_elem<double> { using real = double; using cplx = double2; };
+
+template <typename T>
+__device__ inline void eval_beam(const fv_beam& b, double az, double za, double freq, int fb,
+                                 BeamVal& v) {
+  if (b.kind != 3) {
+    double e;
+    if (b.kind == 0) {
+      const double s = asin(2.2150894 * (kC / freq) / (M_PI * b.diameter)) * 2.0 / 2.355;
+      e = exp(-(za * za) / (2.0 * s * s));
+    } else if (b.kind == 1) {
+      const double x = M_PI * b.diameter * sin(za) * freq / kC;
+      e = (x == 0.0) ? 1.0 : 2.0 * j1(x) / x;
+    } else {
+      e = 1.0;
+    }
+    if (b.is_power) {
+      v.re[0] = e * e; v.im[0] = 0.0;
+    } else {
+      const double q = e / 1.4142135623730951;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { v.re[c] = q; v.im[c] = 0.0; }
+    }
+    return;
+  }
+  // ---- az/za table, mode 'nearest' outside the grid (scipy.ndimage.map_coordinates semantics)
+  double zi = (za - b.za0) / b.dza;
+  double ai = (az - b.az0) / b.daz;
+  if (b.az_wrap_period > 0) {
+    ai = fmod(ai, (double)b.az_wrap_period);
+    if (ai < 0) ai += (double)b.az_wrap_period;
+    ai += (double)b.az_pad;
+  }
+  const int ncomp = b.is_power ? 1 : 4;
+  const int64_t plane = (int64_t)b.nza * b.naz;
+  const int fi = b.freq_offset + fb;
+  int z0, z1, a0, a1;
+  double wz, wa;
+  if (b.order == 0) {
+    z0 = z1 = min(max((int)floor(zi + 0.5), 0), b.nza - 1);
+    a0 = a1 = min(max((int)floor(ai + 0.5), 0), b.naz - 1);
+    wz = wa = 0.0;
+  } else {
+    const double zf = floor(zi), af = floor(ai);
+    wz = zi - zf; wa = ai - af;
+    z0 = min(max((int)zf, 0), b.nza - 1); z1 = min(max((int)zf + 1, 0), b.nza - 1);
+    a0 = min(max((int)af, 0), b.naz - 1); a1 = min(max((int)af + 1, 0), b.naz - 1);
+  }
+  const double w00 = (1 - wz) * (1 - wa), w01 = (1 - wz) * wa, w10 = wz * (1 - wa), w11 = wz * wa;
+  // nfreq_table is implied by the caller's indexing: plane stride per (comp, freq)
+  for (int c = 0; c < ncomp; ++c) {
+    if (b.is_power) {
+      const typename tab_elem<T>::real* t =
+          (const typename tab_elem<T>::real*)b.table + ((int64_t)fi) * plane;
+      v.re[0] = w00 * t[(int64_t)z0 * b.naz + a0] + w01 * t[(int64_t)z0 * b.naz + a1] +
+                w10 * t[(int64_t)z1 * b.naz + a0] + w11 * t[(int64_t)z1 * b.naz + a1];
+      v.im[0] = 0.0;
+    } else {
+      // layout (nfreq_table, 4, nza, naz): the four Jones entries of one frequency are adjacent
+      const typename tab_elem<T>::cplx* t =
+          (const typename tab_elem<T>::cplx*)b.table + ((int64_t)fi * 4 + c) * plane;
+      const auto p00 = t[(int64_t)z0 * b.naz + a0], p01 = t[(int64_t)z0 * b.naz + a1];
+      const auto p10 = t[(int64_t)z1 * b.naz + a0], p11 = t[(int64_t)z1 * b.naz + a1];
+      v.re[c] = w00 * p00.x + w01 * p01.x + w10 * p10.x + w11 * p11.x;
+      v.im[c] = w00 * p00.y + w01 * p01.y + w10 * p10.y + w11 * p11.y;
+    }
+  }
+}
+
+// The four 2x2 products of the reference (cpu/beams.py:129-246), A[b, feed] at index b*2+feed:
+//   mode 1: out[a,p] = sum_b conj(Ai[b,a]) Aj[b,p] F                 (F = Cm[0])
+//   mode 2: out[a,p] = sum_{b,k} conj(Ai'[b,a]) C[b,k] Aj'[k,p],  A'[b] = A[1-b]  (the axis-0 flip
+//           of the polarised-sky branch, cpu_simulate.py:146-147,153)
+//   mode 4: as mode 2 without the flip (the bare numba kernel, cpu/beams.py:147-180,215-246)
+template <typename T>
+__device__ __forceinline__ void coherency_product(int mode, const cplx_t<T>* Ai, const cplx_t<T>* Aj,
+                                                  const cplx_t<T>* Cm, cplx_t<T>* out) {
+  using C = cplx_t<T>;
+  if (mode == 1 || mode == 3) {
+#pragma unroll
+    for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        const C t = cadd(cmulc(Ai[0 * 2 + aa], Aj[0 * 2 + pp]), cmulc(Ai[1 * 2 + aa], Aj[1 * 2 + pp]));
+        out[aa * 2 + pp] = cmul(t, Cm[0]);
+      }
+    return;
+  }
+  const int fl = mode == 2 ? 1 : 0;
+  C tmp[4];   // tmp[a,k] = sum_b conj(Fi[b,a]) C[b,k]
+#pragma unroll
+  for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+      tmp[aa * 2 + kk] = cadd(cmulc(Ai[(0 ^ fl) * 2 + aa], Cm[0 * 2 + kk]), cmulc(Ai[(1 ^ fl) * 2 + aa], Cm[1 * 2 + kk]));
+#pragma unroll
+  for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp)
+      out[aa * 2 + pp] = cadd(cmul(tmp[aa * 2 + 0], Aj[(0 ^ fl) * 2 + pp]), cmul(tmp[aa * 2 + 1], Aj[(1 ^ fl) * 2 + pp]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+weights_kernel(int mode, fv_beam bi, fv_beam bj, int same_beam, const T* __restrict__ az,
+               const T* __restrict__ za, const int32_t* __restrict__ src_idx,
+               const int32_t* __restrict__ n_dev, int64_t n_cap, const double* __restrict__ freqs,
+               int64_t f0, const cplx_t<T>* __restrict__ flux, int64_t nsrc_total,
+               cplx_t<T>* __restrict__ out, cplx_t<T>* __restrict__ out_beam) {
+  using C = cplx_t<T>;
+  const int n = *n_dev;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int fb = blockIdx.y;
+  const double freq = freqs[f0 + fb];
+  const double a = (double)az[s], z = (double)za[s];
+  BeamVal vi, vj;
+  eval_beam<T>(bi, a, z, freq, fb, vi);
+  if (same_beam) vj = vi; else eval_beam<T>(bj, a, z, freq, fb, vj);
+  const int64_t src = src_idx[s];
+  const int P = mode == 0 ? 1 : 4;
+  C* o = out + ((int64_t)fb * P) * n_cap + s;
+  if (out_beam) {
+    const int nc = bi.is_power ? 1 : 4;
+    for (int c = 0; c < nc; ++c)
+      out_beam[((int64_t)fb * nc + c) * n_cap + s] = make_c<T>((T)vi.re[c], (T)vi.im[c]);
+  }
+  if (mode == 0) {
+    // sqrt(B_i B_j) F with the complex principal root (beams were cast to complex first)
+    const T bi_ = (T)vi.re[0], bj_ = (T)vj.re[0];
+    const T p = bi_ * bj_;
+    const C r = p >= T(0) ? make_c<T>(sqrt(p), T(0)) : make_c<T>(T(0), sqrt(-p));
+    o[0] = cmul(r, flux[(int64_t)(f0 + fb) * nsrc_total + src]);
+    return;
+  }
+  C Ai[4], Aj[4], Cm[4], res[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    Ai[c] = make_c<T>((T)vi.re[c], (T)vi.im[c]);
+    Aj[c] = make_c<T>((T)vj.re[c], (T)vj.im[c]);
+  }
+  if (mode == 1) {
+    Cm[0] = flux[(int64_t)(f0 + fb) * nsrc_total + src];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Cm[c] = flux[((int64_t)(f0 + fb) * 4 + c) * nsrc_total + src];
+  }
+  coherency_product<T>(mode, Ai, Aj, Cm, res);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) o[(int64_t)c * n_cap] = res[c];
+}
+
+// stand-alone form of the products (API parity with the CPU evaluator's four methods)
+template <typename T>
+__global__ void __launch_bounds__(256)
+coherency_kernel(int mode, const cplx_t<T>* __restrict__ bi, const cplx_t<T>* __restrict__ bj,
+                 const cplx_t<T>* __restrict__ fc, int64_t n, cplx_t<T>* __restrict__ out) {
+  using C = cplx_t<T>;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  C Ai[4], Aj[4], Cm[4], res[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { Ai[c] = bi[c * n + s]; Aj[c] = bj[c * n + s]; }
+  if (mode == 1 || mode == 3) Cm[0] = fc[s];
+  else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Cm[c] = fc[c * n + s];
+  }
+  coherency_product<T>(mode, Ai, Aj, Cm, res);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c * n + s] = res[c];
+}
+
+static bool same_beam_desc(const fv_beam& a, const fv_beam& b) {
+  return a.kind == b.kind && a.is_power == b.is_power && a.diameter == b.diameter &&
+         a.table == b.table && a.order == b.order && a.freq_offset == b.freq_offset;
+}
+
+}  // namespace fv
+
+extern "C" int fv_weights(int prec, int mode, const fv_beam* beam_i_host, const fv_beam* beam_j_host,
+                          const void* az, const void* za, const int32_t* src_idx,
+                          const int32_t* n_dev, int64_t n_cap, const double* freqs, int nf,
+                          int64_t freq_index0, const void* flux, int64_t nsrc_total, void* out,
+                          void* out_beam_i, void* stream) {
+  FV_REQUIRE(prec == 1 || prec == 2, "prec must be 1 or 2");
+  FV_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+  FV_REQUIRE(beam_i_host && beam_j_host && az && za && src_idx && n_dev && freqs && flux && out,
+             "null pointer");
+  FV_REQUIRE((mode == 0) == (beam_i_host->is_power != 0) && (mode == 0) == (beam_j_host->is_power != 0),
+             "mode 0 needs power beams, modes 1/2 need E-field beams");
+  for (const fv_beam* b : {beam_i_host, beam_j_host}) {
+    FV_REQUIRE(b->kind >= 0 && b->kind <= 3, "unknown beam kind");
+    if (b->kind == 3) {
+      FV_REQUIRE(b->table && b->nza > 0 && b->naz > 0, "table beam without table");
+      if (!(b->order == 0 || b->order == 1)) {
+        fv::set_error("beam interpolation order > 1 is not implemented on the GPU yet");
+        return FV_ERR_UNSUPPORTED;
+      }
+    }
+  }
+  if (nf == 0 || n_cap == 0) return FV_OK;
+  FV_REQUIRE(nf <= 65535, "at most 65535 frequencies per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(fv::ceil_div(n_cap, 256), nf);
+  const int same = fv::same_beam_desc(*beam_i_host, *beam_j_host);
+  if (prec == 1)
+    fv::weights_kernel<float><<<grid, 256, 0, st>>>(
+        mode, *beam_i_host, *beam_j_host, same, (const float*)az, (const float*)za, src_idx, n_dev,
+        n_cap, freqs, freq_index0, (const float2*)flux, nsrc_total, (float2*)out, (float2*)out_beam_i);
+  else
+    fv::weights_kernel<double><<<grid, 256, 0, st>>>(
+        mode, *beam_i_host, *beam_j_host, same, (const double*)az, (const double*)za, src_idx, n_dev,
+        n_cap, freqs, freq_index0, (const double2*)flux, nsrc_total, (double2*)out,
+        (double2*)out_beam_i);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+/* stand-alone apparent-coherency products on caller-supplied beam values (host API parity with
+ * CPUBeamEvaluator.get_apparent_flux_polarized{,_beam,_beam_pair,_pair}, cpu/beams.py:129-246).
+ * mode 1: A_i^H diag(F) A_j;  mode 4: A_i^H C A_j (no flip);  mode 2: with the axis-0 flip.
+ * beams / coherency / out: (4, n) cplx rows [b*2+feed]; flux (n) cplx. */
+extern "C" int fv_coherency(int prec, int mode, const void* beam_i, const void* beam_j,
+                            const void* flux_or_coh, int64_t n, void* out, void* stream) {
+  FV_REQUIRE(prec == 1 || prec == 2, "prec must be 1 or 2");
+  FV_REQUIRE(mode == 1 || mode == 2 || mode == 4, "mode must be 1, 2 or 4");
+  FV_REQUIRE(beam_i && beam_j && flux_or_coh && out, "null pointer");
+  if (n == 0) return FV_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = fv::ceil_div(n, 256);
+  if (prec == 1)
+    fv::coherency_kernel<float><<<blocks, 256, 0, st>>>(mode, (const float2*)beam_i, (const float2*)beam_j, (const float2*)flux_or_coh, n, (float2*)out);
+  else
+    fv::coherency_kernel<double><<<blocks, 256, 0, st>>>(mode, (const double2*)beam_i, (const double2*)beam_j, (const double2*)flux_or_coh, n, (double2*)out);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}

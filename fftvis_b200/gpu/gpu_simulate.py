@@ -1,0 +1,479 @@
+"""GPU simulation engine: fills ``GPUSimulationEngine`` (stub at
+/root/reference/src/fftvis/gpu/gpu_simulate.py:20-91) with the CPU engine's real interface
+(/root/reference/src/fftvis/cpu/cpu_simulate.py:537-569 ``simulate``, :856-884
+``_evaluate_vis_chunk``).
+
+Structure (B200-first, not the reference's per-(time, frequency) Python loop):
+
+* ``simulate``  = host front half (dtype casts, default baselines, gridding / plane rotation;
+  cpu_simulate.py:583-681)  ->  ``SimulationPlan`` (everything uploaded once: catalogue unit
+  vectors, frequency-major fluxes, baseline tables per beam pair, beam tables)  ->
+  ``run_plan`` (device-only loop)  ->  one D2H of the finished ``(nf, nt, [2, 2,] nbls)`` array.
+* ``run_plan`` per time step: ONE fused rotate + horizon-cut + compaction + az/za + array-plane
+  rotation pass (``fv_rotate_cut``); then, per *batch of frequencies* (they share the
+  above-horizon source set, the NU points differ only by the scalar frequency): beam evaluation
+  + apparent coherency (``fv_weights``) and a frequency-batched NUFFT whose epilogue applies the
+  flipped-baseline conjugation, the feed-axis swap and the scatter into the output array in its
+  final layout (``fv_nufft2d1`` for gridded arrays, ``fv_nufft3`` otherwise).  The live source
+  count never leaves the device, so a whole time step is enqueued without host synchronisation
+  on the type-1 path (type 3 reads the NU-point extents back once per time step to size its
+  grids, as finufft does inside every call).
+
+No CPU fallback: every entry point raises ``FVError`` without the CUDA library or a GPU.
+"""
+from __future__ import annotations
+
+import logging
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from ..beam_models import as_beam_model
+from ..core import antenna_gridding, catalog, coords
+from ..core import utils as core_utils
+from ..core.simulate import SimulationEngine, default_accuracy_dict
+from . import _lib
+from .beams import DeviceBeam, GPUBeamEvaluator, launch_weights
+from .nufft import NufftPlan
+
+logger = logging.getLogger(__name__)
+
+_RDT = {1: torch.float32, 2: torch.float64}
+_CDT = {1: torch.complex64, 2: torch.complex128}
+_NP_R = {1: np.float32, 2: np.float64}
+_NP_C = {1: np.complex64, 2: np.complex128}
+_FEED_SWAP = (0, 2, 1, 3)     # transform [a*2+p] -> output slot [p*2+a]  (cpu_simulate.py:300)
+
+
+@dataclass
+class _PairTable:
+    """Device tables of one unique beam pair (cpu/beams.py:91-127 routing)."""
+    bi: int
+    bj: int
+    nk: int
+    kmap: torch.Tensor | None          # int32 baseline indices (None: all baselines in order)
+    conj: torch.Tensor | None          # uint8 flipped flags (None: none flipped)
+    m1: torch.Tensor | None = None     # type 1: signed integer modes (flip already applied)
+    m2: torch.Tensor | None = None
+    uvw: list | None = None            # type 3: per-unit-frequency targets (flip already applied)
+    ulim: list | None = None           # type 3: {min, max} of each target coordinate
+
+
+@dataclass
+class SimulationPlan:
+    """Device-resident state of one ``simulate`` call (or one rank's frequency shard of it)."""
+    precision: int
+    polarized: bool
+    polarized_sky: bool
+    nfeeds: int
+    eps: float
+    upsample_factor: float
+    use_type1: bool
+    is_coplanar: bool
+    n_modes: int | None
+    nbls: int
+    nsrc: int
+    nchunks: int
+    n_cap: int
+    freqs_host: np.ndarray             # working-precision frequencies (ALL of them)
+    f_lo: int
+    f_hi: int
+    enu_mats: np.ndarray               # (nt, 3, 3) fp64
+    plane_mat: np.ndarray              # (3, 3) working precision, as fp64
+    eq_xyz: torch.Tensor               # (3, nsrc) fp64
+    flux: torch.Tensor                 # (nf_total, nsrc) or (nf_total, 4, nsrc) cplx
+    freqs_dev: torch.Tensor            # (nf_total,) fp64 of the working-precision values
+    beams: list                        # DeviceBeam per beam_list entry
+    pairs: list                        # _PairTable per unique beam pair (standard path)
+    basis: dict | None                 # basis path: coefs (nant, K, nf), ant1, ant2
+    freq_batch: int
+    device: torch.device
+    work: dict = field(default_factory=dict)
+
+    @property
+    def ntimes(self) -> int:
+        return self.enu_mats.shape[0]
+
+    @property
+    def nf_local(self) -> int:
+        return self.f_hi - self.f_lo
+
+
+def _next235even(n: int) -> int:
+    return int(_lib.lib().fv_next235even(int(n)))
+
+
+class GPUSimulationEngine(SimulationEngine):
+    """GPU implementation of the simulation engine."""
+
+    def __init__(self, device=None, freq_batch: int | None = None, grid_budget_bytes: int = 48 << 20):
+        self.device = device
+        self.freq_batch = freq_batch
+        self.grid_budget_bytes = int(grid_budget_bytes)
+        self.last_fft_ms = None
+        self._nufft = None
+
+    # ------------------------------------------------------------------------------------------
+    def _device(self) -> torch.device:
+        _lib.require_gpu()
+        if self.device is not None:
+            return torch.device(self.device)
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def _nufft_plan(self, dev) -> NufftPlan:
+        if self._nufft is None or self._nufft.device != dev:
+            with torch.cuda.device(dev):
+                self._nufft = NufftPlan(dev)
+        return self._nufft
+
+    # ------------------------------------------------------------------------------------------
+    def prepare(self, ants, freqs, fluxes, beam_list, ra, dec, times, telescope_loc,
+                baselines=None, beam_idx=None, precision=2, polarized=False, eps=None,
+                upsample_factor=2, beam_spline_opts=None, flat_array_tol=1e-6,
+                coord_method_params=None, force_use_type3=False, nchunks=1, source_buffer=1.0,
+                beam_coefs=None, freq_range=None) -> SimulationPlan:
+        """Host front half of ``simulate`` (cpu_simulate.py:583-709) + upload of every input.
+        ``freq_range=(lo, hi)`` restricts the plan to that slice of ``freqs`` (one rank's shard)."""
+        dev = self._device()
+        if precision not in (1, 2):
+            raise ValueError("precision must be 1 or 2")
+        rd, cd = _NP_R[precision], _NP_C[precision]
+        nfreqs = int(np.size(freqs))
+        nbeam, nant = len(beam_list), len(ants)
+        if eps is None:
+            eps = default_accuracy_dict[precision]
+        ra = np.asarray(ra).astype(rd, copy=False)
+        dec = np.asarray(dec).astype(rd, copy=False)
+        freqs = np.atleast_1d(np.asarray(freqs)).astype(rd, copy=False)
+        beam_idx = core_utils.validate_beam_idx(beam_idx, beam_coefs, nbeam, nant)
+        if beam_coefs is not None and not polarized:
+            raise ValueError(
+                "Basis decomposition is not compatible with unpolarized simulations. "
+                "Set polarized=True to use beam_coefs.")
+        ants = {k: np.asarray(v, dtype=float) for k, v in ants.items()}
+        if baselines is None:
+            baselines = [red[0] for red in core_utils.get_pos_reds(ants, include_autos=True)]
+        baselines = [tuple(b) for b in baselines]
+        nbls = len(baselines)
+        coherency, pol_sky = catalog.prepare_source_catalog(np.asarray(fluxes), polarized_beam=polarized)
+        nsrc = int(np.size(dec))
+
+        # ---- array geometry: gridded -> type 1; else plane rotation -> type 3 (:628-681)
+        antnums = list(ants.keys())
+        a_index = {a: i for i, a in enumerate(antnums)}
+        antvecs = np.array([ants[a] for a in antnums], dtype=rd)
+        basis_matrix, n_modes = None, None
+        if np.abs(antvecs[:, -1]).max() > flat_array_tol or force_use_type3:
+            is_gridded = False
+        else:
+            is_gridded, gridded, basis_matrix = antenna_gridding.check_antpos_griddability(ants)
+        i0 = np.array([a_index[b[0]] for b in baselines], dtype=np.int64)
+        i1 = np.array([a_index[b[1]] for b in baselines], dtype=np.int64)
+        if not is_gridded:
+            rot = np.ascontiguousarray(core_utils.get_plane_to_xy_rotation_matrix(antvecs).T)
+            rants = np.dot(rot, antvecs.T)
+            bls = (rants[:, i1] - rants[:, i0]) if nbls else np.zeros((3, 0))
+            is_coplanar = bool(np.all(np.abs(bls[2]) <= flat_array_tol))
+            bls = (bls / core_utils.speed_of_light).astype(rd)
+            plane = rot.astype(rd)
+        else:
+            logger.info("Using gridded coordinates for the array. Type 1 transform will be used.")
+            gpos = np.array([gridded[a] for a in antnums])
+            bls = np.round(gpos[i1] - gpos[i0]).astype(int).T
+            n_modes = 2 * int(np.round(np.max(np.abs(bls)))) + 1 if nbls else 1
+            plane = (basis_matrix / core_utils.speed_of_light).astype(rd).T
+            is_coplanar = True
+
+        # ---- per-time rotation matrices (stage a1, host part)
+        params = dict(coord_method_params or {})
+        if "rotation_matrices" in params:
+            enu_mats = np.ascontiguousarray(params["rotation_matrices"], dtype=np.float64)
+        else:
+            enu_mats = coords.eq_to_enu_matrices(times, telescope_loc)
+        eq = params.get("eq_xyz")
+        if eq is None:
+            eq = coords.equatorial_unit_vectors(ra, dec)
+        eq = np.ascontiguousarray(eq, dtype=np.float64)
+
+        f_lo, f_hi = (0, nfreqs) if freq_range is None else (int(freq_range[0]), int(freq_range[1]))
+        nchunks = max(1, min(int(nchunks), max(nsrc, 1)))
+        chunk_size = int(math.ceil(nsrc / nchunks)) if nsrc else 0
+        n_cap = max(1, int(chunk_size * source_buffer))
+
+        with torch.cuda.device(dev):
+            rdt, cdt = _RDT[precision], _CDT[precision]
+            eq_d = torch.as_tensor(eq).to(dev)
+            # catalogue, frequency-major so that the gather through ascending src_idx coalesces
+            coh = np.asarray(coherency)
+            if pol_sky:
+                flux_h = np.ascontiguousarray(np.transpose(coh, (1, 2, 3, 0)).reshape(nfreqs, 4, nsrc))
+            else:
+                flux_h = np.ascontiguousarray(coh.T)
+            flux_d = torch.as_tensor(flux_h).to(dev).to(cdt)
+            freqs_d = torch.as_tensor(freqs.astype(np.float64)).to(dev)
+
+            order = int((beam_spline_opts or {}).get("order", 1))
+            models = []
+            for b in beam_list:
+                m = as_beam_model(b)
+                if not polarized and m.beam_type != "power":
+                    m = m.to_power()
+                if polarized and m.beam_type == "power":
+                    raise ValueError("polarized=True needs E-field beams")
+                if hasattr(m, "interp_freq") and m.Nfreqs > 1:
+                    m = m.interp_freq(freqs.astype(np.float64))
+                models.append(m)
+            dbeams = [DeviceBeam(m, precision, order, dev) for m in models]
+
+            pairs, basis = [], None
+            if beam_coefs is not None:
+                coefs = np.asarray(beam_coefs)
+                if coefs.ndim == 2:
+                    coefs = np.repeat(coefs[:, :, None], nfreqs, axis=2)
+                if coefs.shape != (nant, nbeam, nfreqs):
+                    raise ValueError("beam_coefs must have shape (nant, K, nfreqs)")
+                basis = dict(
+                    coefs=torch.as_tensor(np.ascontiguousarray(coefs)).to(dev).to(cdt),
+                    ant1=torch.as_tensor(i0.astype(np.int32)).to(dev),
+                    ant2=torch.as_tensor(i1.astype(np.int32)).to(dev), K=nbeam, nant=nant)
+                pairs.append(self._pair_table(0, 0, np.arange(nbls), np.zeros(nbls, bool), bls,
+                                              is_gridded, is_coplanar, rd, dev, nbls))
+            else:
+                upairs, to_bls, to_flip = GPUBeamEvaluator.prepare_beam_evaluation(antnums, baselines, beam_idx)
+                for (bi, bj) in upairs:
+                    idx = np.asarray(to_bls[(bi, bj)], dtype=np.int64)
+                    if idx.size == 0:
+                        continue
+                    fl = np.asarray(to_flip[(bi, bj)], dtype=bool)
+                    pairs.append(self._pair_table(int(bi), int(bj), idx, fl, bls, is_gridded,
+                                                  is_coplanar, rd, dev, nbls))
+
+        P = 4 if polarized else 1
+        fb = self.freq_batch
+        if fb is None:
+            fb = self._auto_batch(is_gridded, n_modes, P, precision, eps, float(upsample_factor), n_cap)
+        return SimulationPlan(
+            precision=precision, polarized=polarized, polarized_sky=pol_sky, nfeeds=2 if polarized else 1,
+            eps=float(eps), upsample_factor=float(upsample_factor), use_type1=is_gridded,
+            is_coplanar=is_coplanar, n_modes=n_modes, nbls=nbls, nsrc=nsrc, nchunks=nchunks, n_cap=n_cap,
+            freqs_host=freqs, f_lo=f_lo, f_hi=f_hi, enu_mats=enu_mats,
+            plane_mat=np.ascontiguousarray(plane, dtype=np.float64), eq_xyz=eq_d, flux=flux_d,
+            freqs_dev=freqs_d, beams=dbeams, pairs=pairs, basis=basis, freq_batch=int(fb), device=dev)
+
+    @staticmethod
+    def _pair_table(bi, bj, idx, fl, bls, is_gridded, is_coplanar, rd, dev, nbls) -> _PairTable:
+        all_in_order = idx.size == nbls and np.array_equal(idx, np.arange(nbls))
+        kmap = None if all_in_order else torch.as_tensor(idx.astype(np.int32)).to(dev)
+        conj = torch.as_tensor(fl.astype(np.uint8)).to(dev) if fl.any() else None
+        pt = _PairTable(bi=bi, bj=bj, nk=int(idx.size), kmap=kmap, conj=conj)
+        if is_gridded:
+            m = np.where(fl, -bls[:, idx], bls[:, idx])            # cpu_simulate.py:259
+            pt.m1 = torch.as_tensor(np.ascontiguousarray(m[0]).astype(np.int32)).to(dev)
+            pt.m2 = torch.as_tensor(np.ascontiguousarray(m[1]).astype(np.int32)).to(dev)
+        else:
+            q = np.where(fl, -bls[:, idx], bls[:, idx]).astype(rd)  # cpu_simulate.py:271
+            dim = 2 if is_coplanar else 3
+            pt.uvw = [torch.as_tensor(np.ascontiguousarray(q[d])).to(dev) for d in range(dim)]
+            pt.ulim = [float(v) for d in range(dim) for v in (q[d].min(), q[d].max())]
+        return pt
+
+    def _auto_batch(self, type1, n_modes, P, precision, eps, upsampfac, n_cap) -> int:
+        """Frequencies per batch: keep the batch's fine grids near the L2 budget."""
+        csize = 8 * precision
+        if type1:
+            import ctypes
+            w = ctypes.c_int(0); beta = ctypes.c_double(0)
+            _lib.check(_lib.lib().fv_kernel_params(eps, upsampfac, precision, ctypes.byref(w), ctypes.byref(beta)))
+            nf = _next235even(max(int(upsampfac * n_modes), 2 * w.value))
+            per_f = P * nf * nf * csize
+        else:
+            per_f = self.grid_budget_bytes      # type-3 grids are large: one or a few per batch
+        by_grid = max(1, self.grid_budget_bytes // max(per_f, 1))
+        by_w = max(1, (1 << 30) // max(1, P * n_cap * csize))          # strengths buffer <= 1 GiB
+        return int(max(1, min(256, by_grid, by_w)))
+
+    # ------------------------------------------------------------------------------------------
+    def _workspace(self, plan: SimulationPlan):
+        if plan.work:
+            return plan.work
+        dev, prec = plan.device, plan.precision
+        rdt, cdt = _RDT[prec], _CDT[prec]
+        P = 4 if plan.polarized else 1
+        n_cap, nb = plan.n_cap, plan.freq_batch
+        w = plan.work
+        w["xyz"] = torch.empty((3, n_cap), dtype=rdt, device=dev)
+        w["az"] = torch.empty(n_cap, dtype=rdt, device=dev)
+        w["za"] = torch.empty(n_cap, dtype=rdt, device=dev)
+        w["src_idx"] = torch.empty(n_cap, dtype=torch.int32, device=dev)
+        w["n_dev"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        w["counts"] = torch.zeros((plan.ntimes, plan.nchunks), dtype=torch.int32, device=dev)
+        sb = int(_lib.lib().fv_rotate_cut_scratch_bytes(max(plan.nsrc, 1)))
+        w["scratch"] = torch.empty(sb, dtype=torch.uint8, device=dev)
+        w["W"] = torch.empty((nb, P, n_cap), dtype=cdt, device=dev)
+        if plan.basis is not None:
+            w["vkl"] = torch.empty((nb, 4, plan.nbls), dtype=cdt, device=dev)
+        return w
+
+    def run_plan(self, plan: SimulationPlan, out: torch.Tensor | None = None,
+                 time_range=None) -> torch.Tensor:
+        """Device-only hot loop (the GPU form of ``_evaluate_vis_chunk``, cpu_simulate.py:936-1069).
+        Returns the device tensor ``(nf_local, nt, P, nbls)`` in the final output layout."""
+        dev, prec = plan.device, plan.precision
+        L = _lib.lib()
+        P = 4 if plan.polarized else 1
+        nt_all = plan.ntimes
+        t_lo, t_hi = (0, nt_all) if time_range is None else time_range
+        nt = t_hi - t_lo
+        nfl = plan.nf_local
+        cdt = _CDT[prec]
+        with torch.cuda.device(dev):
+            nufft = self._nufft_plan(dev)
+            st = torch.cuda.current_stream()
+            if nufft.stream.cuda_stream != st.cuda_stream:
+                raise RuntimeError("run_plan must run on the stream its NUFFT plan was created on")
+            if out is None:
+                out = torch.zeros((nfl, nt, P, plan.nbls), dtype=cdt, device=dev)
+            else:
+                out.zero_()
+            if nfl == 0 or nt == 0 or plan.nbls == 0 or plan.nsrc == 0:
+                return out
+            w = self._workspace(plan)
+            esz = out.element_size()
+            mode = 0 if not plan.polarized else (2 if plan.polarized_sky else 1)
+            pmap = _FEED_SWAP if plan.polarized else (0, 1, 2, 3)
+            dim = 2 if (plan.use_type1 or plan.is_coplanar) else 3
+            chunk = int(math.ceil(plan.nsrc / plan.nchunks))
+            freqs64 = plan.freqs_host.astype(np.float64)
+            for to, ti in enumerate(range(t_lo, t_hi)):
+                for ch in range(plan.nchunks):
+                    lo, hi = ch * chunk, min(plan.nsrc, (ch + 1) * chunk)
+                    if lo >= hi:
+                        continue
+                    _lib.check(L.fv_rotate_cut(
+                        prec, plan.eq_xyz.data_ptr(), plan.nsrc, lo, hi,
+                        _lib.doubles(plan.enu_mats[ti].ravel()), _lib.doubles(plan.plane_mat.ravel()),
+                        w["xyz"].data_ptr(), w["az"].data_ptr(), w["za"].data_ptr(),
+                        w["src_idx"].data_ptr(), plan.n_cap, w["n_dev"].data_ptr(),
+                        w["scratch"].data_ptr(), st.cuda_stream), "fv_rotate_cut")
+                    w["counts"][ti, ch:ch + 1].copy_(w["n_dev"])
+                    xlim = None
+                    if not plan.use_type1:
+                        import ctypes
+                        lim = (ctypes.c_double * 6)()
+                        _lib.check(L.fv_minmax(nufft.handle, prec, dim, w["xyz"][0].data_ptr(),
+                                               w["xyz"][1].data_ptr(), w["xyz"][2].data_ptr(),
+                                               w["n_dev"].data_ptr(), 0, lim), "fv_minmax")
+                        xlim = [lim[i] for i in range(2 * dim)]
+                        if not (xlim[0] <= xlim[1]):
+                            continue                         # nothing above the horizon
+                    for f0 in range(plan.f_lo, plan.f_hi, plan.freq_batch):
+                        nb = min(plan.freq_batch, plan.f_hi - f0)
+                        scale = freqs64[f0:f0 + nb]
+                        obase = out.data_ptr() + ((f0 - plan.f_lo) * nt + to) * P * plan.nbls * esz
+                        sb_, sp_ = nt * P * plan.nbls, plan.nbls
+                        if plan.basis is not None:
+                            self._basis_batch(plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st)
+                            continue
+                        for pt in plan.pairs:
+                            launch_weights(prec, mode, plan.beams[pt.bi], plan.beams[pt.bj], w["az"], w["za"],
+                                           w["src_idx"], w["n_dev"], plan.n_cap, plan.freqs_dev, f0, nb,
+                                           plan.flux, plan.nsrc, w["W"], None, st)
+                            epi = _lib.make_epilogue(
+                                obase, sb_, sp_, pmap, pt.kmap.data_ptr() if pt.kmap is not None else 0,
+                                pt.conj.data_ptr() if pt.conj is not None else 0, accumulate=True)
+                            self._nufft_batch(plan, w, nufft, pt, dim, xlim, scale, nb, epi)
+            return out
+
+    def _nufft_batch(self, plan, w, nufft, pt, dim, xlim, scale, nb, epi):
+        W = w["W"][:nb]
+        if plan.use_type1:
+            nufft.type1(plan.precision, w["xyz"][0], w["xyz"][1], w["n_dev"], scale, W, plan.n_modes,
+                        pt.m1, pt.m2, plan.eps, plan.upsample_factor, epi)
+        else:
+            nufft.type3(plan.precision, dim, w["xyz"], w["n_dev"], xlim, pt.uvw, pt.ulim, scale, W,
+                        plan.eps, plan.upsample_factor, epi)
+
+    def _basis_batch(self, plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st):
+        """K (K + 1) / 2 transforms over all baselines + contraction (cpu_simulate.py:416-468)."""
+        import ctypes
+        L = _lib.lib()
+        b = plan.basis
+        pt = plan.pairs[0]
+        vkl = w["vkl"]
+        for k in range(b["K"]):
+            for l in range(k, b["K"]):
+                launch_weights(plan.precision, mode, plan.beams[k], plan.beams[l], w["az"], w["za"],
+                               w["src_idx"], w["n_dev"], plan.n_cap, plan.freqs_dev, f0, nb, plan.flux,
+                               plan.nsrc, w["W"], None, st)
+                epi = _lib.make_epilogue(vkl.data_ptr(), vkl.stride(0), vkl.stride(1), _FEED_SWAP)
+                self._nufft_batch(plan, w, nufft, pt, dim, xlim, scale, nb, epi)
+                epo = _lib.make_epilogue(obase, sb_, sp_, (0, 1, 2, 3), accumulate=True)
+                _lib.check(L.fv_basis_contract(
+                    plan.precision, vkl.data_ptr(), nb, plan.nbls, b["coefs"].data_ptr(), b["nant"], b["K"],
+                    plan.freqs_host.size, f0, k, l, b["ant1"].data_ptr(), b["ant2"].data_ptr(),
+                    ctypes.byref(epo), st.cuda_stream), "fv_basis_contract")
+
+    def check_source_buffer(self, plan: SimulationPlan):
+        """Raise like matvis' ``select_chunk`` when a chunk overflowed its buffer
+        (reference call site cpu_simulate.py:940)."""
+        if not plan.work:
+            return
+        counts = plan.work["counts"].cpu().numpy()
+        if (counts < 0).any():
+            raise ValueError(
+                f"source_buffer too small: {int(-counts.min())} sources above the horizon in one chunk "
+                f"but the buffer holds {plan.n_cap}. Increase source_buffer.")
+
+    # ------------------------------------------------------------------------------------------
+    def simulate(self, ants, freqs, fluxes, beam_list, ra, dec, times, telescope_loc,
+                 baselines=None, beam_idx=None, precision=2, polarized=False, eps=None,
+                 upsample_factor=2, beam_spline_opts=None, flat_array_tol=1e-6,
+                 interpolation_function="az_za_map_coordinates", nprocesses=1, nthreads=None,
+                 coord_method="CoordinateRotationERFA", coord_method_params=None,
+                 force_use_ray=False, force_use_type3=False, trace_mem=False,
+                 enable_memory_monitor=False, nchunks=1, source_buffer=1.0, beam_coefs=None):
+        """Simulate visibilities on the GPU; same parameters and return value as the CPU engine
+        (cpu_simulate.py:537-569, return at :850-854).  ``nprocesses``, ``nthreads``,
+        ``force_use_ray``, ``trace_mem`` and ``enable_memory_monitor`` are CPU-only knobs and are
+        accepted and ignored; ``coord_method`` selects nothing here (see core/coords.py)."""
+        plan = self.prepare(ants, freqs, fluxes, beam_list, ra, dec, times, telescope_loc,
+                            baselines=baselines, beam_idx=beam_idx, precision=precision,
+                            polarized=polarized, eps=eps, upsample_factor=upsample_factor,
+                            beam_spline_opts=beam_spline_opts, flat_array_tol=flat_array_tol,
+                            coord_method_params=coord_method_params, force_use_type3=force_use_type3,
+                            nchunks=nchunks, source_buffer=source_buffer, beam_coefs=beam_coefs)
+        out = self.run_plan(plan)
+        self.check_source_buffer(plan)
+        return self.finish(plan, out)
+
+    @staticmethod
+    def finish(plan: SimulationPlan, out: torch.Tensor) -> np.ndarray:
+        """D2H + final shape ``(nf, nt, 2, 2, nbls)`` / ``(nf, nt, nbls)`` (cpu_simulate.py:850-854)."""
+        res = out.cpu().numpy()
+        nf, nt = res.shape[0], res.shape[1]
+        if plan.polarized:
+            return res.reshape(nf, nt, 2, 2, plan.nbls)
+        return res.reshape(nf, nt, plan.nbls)
+
+    # ------------------------------------------------------------------------------------------
+    def _evaluate_vis_chunk(self, time_idx, freq_idx, plan: SimulationPlan = None, **kwargs):
+        """One (time-slice, frequency-slice) block as ``(nt_here, nbls, nfeed, nfeed, nf_here)``
+        (cpu_simulate.py:856-1071).  The GPU engine's unit of state is the device-resident
+        ``SimulationPlan`` (from ``prepare``) instead of the CPU engine's coord_mgr / bls / beam
+        arguments."""
+        if plan is None:
+            raise TypeError("GPUSimulationEngine._evaluate_vis_chunk needs plan=<SimulationPlan from prepare()>")
+        nt_all, nf_all = plan.ntimes, plan.freqs_host.size
+        ts = range(nt_all)[time_idx]
+        fs = range(nf_all)[freq_idx]
+        if len(ts) == 0 or len(fs) == 0:
+            return np.zeros((len(ts), plan.nbls, plan.nfeeds, plan.nfeeds, len(fs)), _NP_C[plan.precision])
+        if ts.step != 1 or fs.step != 1:
+            raise ValueError("time_idx / freq_idx must be contiguous slices")
+        sub = SimulationPlan(**{**plan.__dict__, "f_lo": fs.start, "f_hi": fs.stop, "work": plan.work})
+        out = self.run_plan(sub, time_range=(ts.start, ts.stop))
+        self.check_source_buffer(sub)
+        res = out.cpu().numpy().reshape(len(fs), len(ts), plan.nfeeds, plan.nfeeds, plan.nbls)
+        return np.ascontiguousarray(np.transpose(res, (1, 4, 2, 3, 0)))

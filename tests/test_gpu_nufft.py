@@ -1,0 +1,198 @@
+"""GPU NUFFTs through the C ABI vs the oracle (fp64 direct sum + CPU NUFFT restatement).
+Tolerance: relative L2 error <= 10 x eps in fp64 (north_star); in fp32 the floor is the rounding
+of the *inputs* (phases up to ~60 rad carry ~4e-6 rad of fp32 rounding), so the bar there is the
+oracle's own fp32 error x 3 (SURVEY.md section 7 "fp32 parity floor")."""
+import numpy as np
+import pytest
+
+from gpu_helpers import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _types(prec):
+    return (np.float32, np.complex64) if prec == 1 else (np.float64, np.complex128)
+
+
+@pytest.mark.parametrize("prec,eps", [(2, 1e-13), (2, 1e-10), (2, 1e-6), (1, 6e-8), (1, 1e-4)])
+@pytest.mark.parametrize("upsamp", [2.0, 1.25])
+@pytest.mark.parametrize("ntr", [1, 4])
+def test_type1_vs_oracle(prec, eps, upsamp, ntr):
+    from fftvis_b200.gpu import gpu_nufft2d_type1
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(0)
+    n, N = 700, 21
+    rd, cd = _types(prec)
+    x = rng.uniform(-40, 40, n).astype(rd)
+    y = rng.uniform(-40, 40, n).astype(rd)
+    c = (rng.normal(size=(ntr, n)) + 1j * rng.normal(size=(ntr, n))).astype(cd)
+    idx = rng.integers(-(N // 2), N // 2 + 1, size=(2, 97))
+    got = gpu_nufft2d_type1(x, y, c, N, idx, eps, upsample_factor=upsamp)
+    assert got.shape == (ntr, 97) and got.dtype == cd
+    want = nc.direct_sum(x, y, None, c, idx[0], idx[1], None)
+    cpu = nc.cpu_nufft2d_type1(x, y, c, N, idx, eps, upsamp)
+    floor = 1e-9 if upsamp == 1.25 else 0.0
+    if prec == 2:
+        assert relerr(got, want) < max(10 * eps, floor)
+    else:
+        assert relerr(got, want) < max(10 * eps, 3 * relerr(cpu, want), 3e-5)
+    assert relerr(got, cpu) < max(10 * eps, floor, 3e-5 if prec == 1 else 0)
+
+
+@pytest.mark.parametrize("prec,eps", [(2, 1e-13), (2, 1e-10), (1, 6e-8)])
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("upsamp", [2.0, 1.25])
+def test_type3_vs_oracle(prec, eps, dim, upsamp):
+    from fftvis_b200.gpu import gpu_nufft2d, gpu_nufft3d
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(1)
+    n, nk = 900, 130
+    rd, cd = _types(prec)
+    lm = rng.uniform(-0.7, 0.7, (2, n))
+    nn = np.sqrt(1 - (lm**2).sum(0))
+    xs = [(2 * np.pi * a).astype(rd) for a in (lm[0], lm[1], nn)][:dim]
+    ss = [rng.uniform(-12, 12, nk).astype(rd), rng.uniform(-12, 12, nk).astype(rd),
+          rng.uniform(-0.5, 0.5, nk).astype(rd)][:dim]
+    c = (rng.normal(size=(2, n)) + 1j * rng.normal(size=(2, n))).astype(cd)
+    if dim == 2:
+        got = gpu_nufft2d(xs[0], xs[1], c, ss[0], ss[1], eps, upsample_factor=upsamp)
+    else:
+        got = gpu_nufft3d(xs[0], xs[1], xs[2], c, ss[0], ss[1], ss[2], eps, upsample_factor=upsamp)
+    want = nc.direct_sum(xs[0], xs[1], xs[2] if dim == 3 else None, c, ss[0], ss[1],
+                         ss[2] if dim == 3 else None)
+    floor = 1e-9 if upsamp == 1.25 else 0.0
+    tol = max(10 * eps, floor) if prec == 2 else 3e-5
+    assert got.shape == want.shape
+    assert relerr(got, want) < tol
+
+
+def test_type3_offcentre_points_and_targets():
+    """Non-zero centres exercise the pre- and post-phases."""
+    from fftvis_b200.gpu import gpu_nufft3d
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(5)
+    n, nk = 500, 77
+    x, y = rng.uniform(1.0, 3.0, n), rng.uniform(-2.0, -0.5, n)
+    z = rng.uniform(4.0, 6.0, n)
+    u, v, w = rng.uniform(20, 30, nk), rng.uniform(-40, -25, nk), rng.uniform(3, 5, nk)
+    c = rng.normal(size=n) + 1j * rng.normal(size=n)
+    got = gpu_nufft3d(x, y, z, c, u, v, w, 1e-12)
+    want = nc.direct_sum(x, y, z, c, u, v, w)
+    assert got.shape == (nk,)
+    assert relerr(got, want) < 1e-11
+
+
+def test_single_point_and_single_target():
+    from fftvis_b200.gpu import gpu_nufft2d
+    got = gpu_nufft2d(np.array([0.3]), np.array([-0.2]), np.array([2.0 + 1j]), np.array([5.0]),
+                      np.array([-3.0]), 1e-12)
+    want = (2.0 + 1j) * np.exp(1j * (5.0 * 0.3 + 3.0 * 0.2))
+    assert abs(got[0] - want) < 1e-10
+
+
+def test_empty_inputs():
+    from fftvis_b200.gpu import gpu_nufft2d, gpu_nufft2d_type1
+    e = np.zeros(0)
+    out = gpu_nufft2d(e, e, np.zeros(0, complex), np.array([1.0, 2.0]), np.array([0.5, 0.1]), 1e-10)
+    assert out.shape == (2,) and np.all(out == 0)
+    out = gpu_nufft2d_type1(e, e, np.zeros((4, 0), complex), 7, np.array([[0, 1], [2, -3]]), 1e-10)
+    assert out.shape == (4, 2) and np.all(out == 0)
+
+
+def test_type1_mode_out_of_range_raises():
+    from fftvis_b200.gpu import gpu_nufft2d_type1
+    x = np.array([0.1, 0.2])
+    with pytest.raises(IndexError):
+        gpu_nufft2d_type1(x, x, np.ones(2, complex), 7, np.array([[9], [0]]), 1e-10)
+
+
+def test_frequency_batched_type1_and_type3_match_one_by_one():
+    """The batch dimension (frequencies sharing one source set) against per-frequency calls."""
+    import torch
+    from fftvis_b200.gpu import _lib
+    from fftvis_b200.gpu.nufft import default_plan
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(7)
+    n, nk, nb, ntr = 1500, 64, 5, 4
+    bx, by = rng.uniform(-0.3, 0.3, n), rng.uniform(-0.3, 0.3, n)
+    scale = np.linspace(100.0, 200.0, nb)
+    W = rng.normal(size=(nb, ntr, n)) + 1j * rng.normal(size=(nb, ntr, n))
+    m = rng.integers(-10, 11, size=(2, nk))
+    dev = "cuda"
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to(dev, dt)
+    n_dev = torch.tensor([n], dtype=torch.int32, device=dev)
+    out = torch.zeros((nb, ntr, nk), dtype=torch.complex128, device=dev)
+    epi = _lib.make_epilogue(out.data_ptr(), out.stride(0), out.stride(1))
+    plan = default_plan()
+    plan.type1(2, t(bx, torch.float64), t(by, torch.float64), n_dev, scale, t(W, torch.complex128), 21,
+               t(m[0], torch.int32), t(m[1], torch.int32), 1e-12, 2.0, epi)
+    got = out.cpu().numpy()
+    for b in range(nb):
+        want = nc.direct_sum(bx * scale[b], by * scale[b], None, W[b], m[0], m[1], None)
+        assert relerr(got[b], want) < 1e-11
+    # type 3: targets scale with the frequency
+    x = [2 * np.pi * rng.uniform(-0.6, 0.6, n) for _ in range(2)]
+    u = [rng.uniform(-0.08, 0.08, nk) for _ in range(2)]
+    out.zero_()
+    plan.type3(2, 2, [t(a, torch.float64) for a in x], n_dev, None, [t(a, torch.float64) for a in u], None,
+               scale, t(W, torch.complex128), 1e-12, 2.0, epi)
+    got = out.cpu().numpy()
+    for b in range(nb):
+        want = nc.direct_sum(x[0], x[1], None, W[b], u[0] * scale[b], u[1] * scale[b], None)
+        assert relerr(got[b], want) < 1e-11
+
+
+def test_epilogue_conj_kmap_pmap_accumulate():
+    import torch
+    from fftvis_b200.gpu import _lib
+    from fftvis_b200.gpu.nufft import default_plan
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(8)
+    n, nk = 300, 10
+    x = [2 * np.pi * rng.uniform(-0.6, 0.6, n) for _ in range(2)]
+    u = [rng.uniform(-8, 8, nk) for _ in range(2)]
+    W = rng.normal(size=(1, 4, n)) + 1j * rng.normal(size=(1, 4, n))
+    kmap = rng.permutation(16)[:nk].astype(np.int32)
+    conj = (rng.uniform(size=nk) < 0.5).astype(np.uint8)
+    dev = "cuda"
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to(dev, dt)
+    out = torch.ones((1, 4, 16), dtype=torch.complex128, device=dev)
+    km, cj = t(kmap, torch.int32), t(conj, torch.uint8)
+    epi = _lib.make_epilogue(out.data_ptr(), out.stride(0), out.stride(1), (0, 2, 1, 3), km.data_ptr(),
+                             cj.data_ptr(), accumulate=True)
+    n_dev = torch.tensor([n], dtype=torch.int32, device=dev)
+    default_plan().type3(2, 2, [t(a, torch.float64) for a in x], n_dev, None,
+                         [t(a, torch.float64) for a in u], None, [1.0], t(W, torch.complex128), 1e-12, 2.0, epi)
+    got = out.cpu().numpy()[0]
+    ref = nc.direct_sum(x[0], x[1], None, W[0], u[0], u[1], None)
+    ref = np.where(conj[None, :].astype(bool), ref.conj(), ref)
+    want = np.ones((4, 16), complex)
+    for p, slot in enumerate((0, 2, 1, 3)):
+        want[slot, kmap] += ref[p]
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
+
+
+def test_gpu_direct_sum_matches_oracle():
+    import ctypes
+    import torch
+    from fftvis_b200.gpu import _lib
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(9)
+    n, nk = 257, 33
+    x = [rng.uniform(-3, 3, n) for _ in range(3)]
+    u = [rng.uniform(-20, 20, nk) for _ in range(3)]
+    W = rng.normal(size=(2, 2, n)) + 1j * rng.normal(size=(2, 2, n))
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dt)
+    xs, us = [t(a, torch.float64) for a in x], [t(a, torch.float64) for a in u]
+    Wd = t(W, torch.complex128)
+    out = torch.zeros((2, 2, nk), dtype=torch.complex128, device="cuda")
+    epi = _lib.make_epilogue(out.data_ptr(), out.stride(0), out.stride(1))
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().fv_direct_sum(2, 3, xs[0].data_ptr(), xs[1].data_ptr(), xs[2].data_ptr(),
+                                        n_dev.data_ptr(), n, us[0].data_ptr(), us[1].data_ptr(),
+                                        us[2].data_ptr(), nk, _lib.doubles([1.0, 0.5]), 2, 2, Wd.data_ptr(),
+                                        ctypes.byref(epi), torch.cuda.current_stream().cuda_stream))
+    got = out.cpu().numpy()
+    for b, s in enumerate((1.0, 0.5)):
+        want = nc.direct_sum(x[0], x[1], x[2], W[b], u[0] * s, u[1] * s, u[2] * s)
+        assert relerr(got[b], want) < 1e-13

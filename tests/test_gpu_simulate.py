@@ -1,0 +1,192 @@
+"""End-to-end parity of ``simulate_vis(backend="gpu")`` against the oracle: the reference-structured
+CPU pipeline (oracle.pipeline.simulate_cpu) and the term-by-term fp64 measurement equation
+(oracle.pipeline.simulate_direct).  Mirrors the reference's own integration tests
+(tests/test_cpu_simulate.py:75-271 type-1 == type-3 and vs a direct simulator; tests/test_beam_basis.py
+:310-431 basis == per-antenna; tests/test_wrapper.py:318 f32 ~ f64).
+Bar: relative L2 error <= 10 x eps (fp64); fp32 is limited by input rounding (see test_gpu_nufft)."""
+import numpy as np
+import pytest
+
+from gpu_helpers import TIMES, hex_ants, relerr, small_sky
+
+pytestmark = pytest.mark.gpu
+
+FREQS = np.array([100e6, 110e6])
+
+
+def _cfg1(nsrc=100, polarized_sky=False):
+    from fftvis_b200 import HERA_LOCATION
+    from fftvis_b200 import synth
+    ants = synth.hex_rows((3, 4, 3))        # the 10-antenna hex of BASELINE configs[0]
+    ra, dec, flux = small_sky(nsrc, FREQS, polarized=polarized_sky)
+    return ants, flux, ra, dec, HERA_LOCATION
+
+
+@pytest.mark.parametrize("force3", [False, True])
+@pytest.mark.parametrize("precision,eps", [(2, 1e-13), (2, 1e-10), (1, 6e-8)])
+def test_cfg1_unpolarized_gaussian(precision, eps, force3):
+    """BASELINE configs[0]: 10-antenna hex, 100 sources, 2 freqs, unpolarized Gaussian beam."""
+    from fftvis_b200 import GaussianBeam, simulate_vis
+    from oracle import pipeline
+    ants, flux, ra, dec, loc = _cfg1()
+    beam = GaussianBeam(diameter=14.0)
+    got = simulate_vis(ants, flux, ra, dec, FREQS, TIMES[:1], beam, loc, precision=precision, eps=eps,
+                       force_use_type3=force3)
+    cpu = pipeline.simulate_cpu(ants, flux, ra, dec, FREQS, TIMES[:1], [beam.to_power()], loc,
+                                precision=precision, eps=eps, force_use_type3=force3)
+    direct = pipeline.simulate_direct(ants, flux, ra, dec, FREQS, TIMES[:1], [beam.to_power()], loc,
+                                      precision=precision)
+    assert got.shape == cpu.shape == (2, 1, got.shape[-1])
+    assert got.dtype == (np.complex64 if precision == 1 else np.complex128)
+    if precision == 2:
+        assert relerr(got, direct) < 10 * eps
+        assert relerr(got, cpu) < 10 * eps
+    else:
+        assert relerr(got, direct) < max(3 * relerr(cpu, direct), 1e-5)
+
+
+@pytest.mark.parametrize("force3", [False, True])
+@pytest.mark.parametrize("pol_sky", [False, True])
+def test_polarized_table_beam(pol_sky, force3):
+    from fftvis_b200 import simulate_vis, synth
+    from oracle import pipeline
+    ants, flux, ra, dec, loc = _cfg1(300, polarized_sky=pol_sky)
+    beam = synth.synthetic_uvbeam(FREQS, naz=72, nza=37)
+    kw = dict(precision=2, eps=1e-12, polarized=True, beam_spline_opts={"order": 1}, force_use_type3=force3)
+    got = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beam, loc, **kw)
+    cpu = pipeline.simulate_cpu(ants, flux, ra, dec, FREQS, TIMES, [beam], loc, **kw)
+    assert got.shape == cpu.shape and got.shape[:4] == (2, 2, 2, 2)
+    assert relerr(got, cpu) < 1e-11
+    direct = pipeline.simulate_direct(ants, flux, ra, dec, FREQS, TIMES, [beam], loc, precision=2,
+                                      polarized=True, beam_spline_opts={"order": 1})
+    assert relerr(got, direct) < 1e-11
+
+
+@pytest.mark.parametrize("polarized", [False, True])
+@pytest.mark.parametrize("force3", [False, True])
+def test_per_antenna_beams_with_flipped_pairs(polarized, force3):
+    """Two beam types alternating over antennas, explicit baselines in both orders
+    (reference tests/test_cpu_simulate.py:273-382 uses one un-flipped baseline; cpu/beams.py:115-125)."""
+    from fftvis_b200 import AiryBeam, GaussianBeam, simulate_vis, synth
+    from oracle import pipeline
+    ants, flux, ra, dec, loc = _cfg1(200)
+    nant = len(ants)
+    beam_idx = np.arange(nant) % 2
+    if polarized:
+        beams = [synth.synthetic_uvbeam(FREQS, naz=72, nza=37, seed=s, perturb=0.3) for s in (1, 2)]
+    else:
+        beams = [GaussianBeam(diameter=14.0), AiryBeam(diameter=12.0)]
+    baselines = [(0, 1), (1, 0), (1, 2), (2, 4), (3, 3), (5, 2), (4, 4), (6, 9)]
+    kw = dict(precision=2, eps=1e-12, polarized=polarized, beam_spline_opts={"order": 1},
+              force_use_type3=force3, beam_idx=beam_idx, baselines=baselines)
+    got = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beams, loc, **kw)
+    cpu_beams = beams if polarized else [b.to_power() for b in beams]
+    cpu = pipeline.simulate_cpu(ants, flux, ra, dec, FREQS, TIMES, cpu_beams, loc, **kw)
+    assert relerr(got, cpu) < 1e-11
+
+
+def test_basis_path_matches_per_antenna_path():
+    """reference tests/test_beam_basis.py:310-431 (atol 1e-5 there)."""
+    from fftvis_b200 import simulate_vis, synth
+    from oracle import pipeline
+    ants, flux, ra, dec, loc = _cfg1(150)
+    nant, K = len(ants), 3
+    rng = np.random.default_rng(42)
+    basis = [synth.synthetic_uvbeam(FREQS, naz=72, nza=37, seed=s, perturb=0.3) for s in range(K)]
+    for b in basis:                      # real-valued basis beams: the regime where the reference's
+        b.data_array = b.data_array.real.astype(complex)   # upper-triangle trick is exact
+    coefs = rng.normal(size=(nant, K, FREQS.size)) + 1j * rng.normal(size=(nant, K, FREQS.size))
+    baselines = [(0, 1), (2, 5), (3, 3), (9, 4), (1, 0)]
+    kw = dict(precision=2, eps=1e-12, polarized=True, beam_spline_opts={"order": 1}, baselines=baselines)
+    got = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, basis, loc, beam_coefs=coefs, **kw)
+    cpu = pipeline.simulate_cpu(ants, flux, ra, dec, FREQS, TIMES, basis, loc, beam_coefs=coefs, **kw)
+    assert relerr(got, cpu) < 1e-11
+    direct = pipeline.simulate_direct(ants, flux, ra, dec, FREQS, TIMES, basis, loc, precision=2, polarized=True,
+                                      beam_spline_opts={"order": 1}, beam_coefs=coefs, baselines=baselines)
+    assert relerr(got, direct) < 1e-10
+    got3 = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, basis, loc, beam_coefs=coefs, force_use_type3=True, **kw)
+    assert relerr(got3, got) < 1e-11
+
+
+def test_tilted_nonflat_array_uses_3d_and_matches_direct():
+    from fftvis_b200 import AiryBeam, HERA_LOCATION, simulate_vis, synth
+    from oracle import pipeline
+    ants = synth.random_array(12, radius=60.0, zspan=2.0, seed=42)
+    ra, dec, flux = small_sky(400, FREQS)
+    beam = AiryBeam(diameter=14.0)
+    bls = synth.all_baselines(ants, autos=True)
+    got = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beam, HERA_LOCATION, precision=2, eps=1e-12, baselines=bls)
+    direct = pipeline.simulate_direct(ants, flux, ra, dec, FREQS, TIMES, [beam.to_power()], HERA_LOCATION,
+                                      precision=2, baselines=bls)
+    assert got.shape == (2, 2, len(bls))
+    assert relerr(got, direct) < 1e-11
+    # tilted but flat plane: rotation to the xy plane then the 2-D transform
+    tilt = {k: np.array([v[0], v[1], 0.02 * v[0] - 0.01 * v[1]]) for k, v in ants.items()}
+    got = simulate_vis(tilt, flux, ra, dec, FREQS, TIMES, beam, HERA_LOCATION, precision=2, eps=1e-12, baselines=bls)
+    direct = pipeline.simulate_direct(tilt, flux, ra, dec, FREQS, TIMES, [beam.to_power()], HERA_LOCATION,
+                                      precision=2, baselines=bls)
+    assert relerr(got, direct) < 1e-11
+
+
+def test_source_chunks_and_frequency_batches_do_not_change_the_answer():
+    from fftvis_b200 import GaussianBeam, HERA_LOCATION
+    from fftvis_b200.gpu import GPUSimulationEngine
+    ants = hex_ants(3)
+    freqs = np.linspace(100e6, 120e6, 7)
+    ra, dec, flux = small_sky(1000, freqs)
+    beam = GaussianBeam(diameter=14.0).to_power()
+    args = (ants, freqs, flux, [beam], ra, dec, TIMES, HERA_LOCATION)
+    base = GPUSimulationEngine().simulate(*args, precision=2, eps=1e-12)
+    chunked = GPUSimulationEngine(freq_batch=3).simulate(*args, precision=2, eps=1e-12, nchunks=3, source_buffer=1.0)
+    assert relerr(chunked, base) < 1e-12
+    with pytest.raises(ValueError, match="source_buffer"):
+        GPUSimulationEngine().simulate(*args, precision=2, eps=1e-12, nchunks=1, source_buffer=0.3)
+
+
+def test_evaluate_vis_chunk_slices_match_simulate():
+    from fftvis_b200 import GaussianBeam, HERA_LOCATION
+    from fftvis_b200.gpu import GPUSimulationEngine
+    ants = hex_ants(2)
+    freqs = np.linspace(100e6, 120e6, 5)
+    ra, dec, flux = small_sky(200, freqs)
+    eng = GPUSimulationEngine()
+    beam = GaussianBeam(diameter=14.0).to_power()
+    full = eng.simulate(ants, freqs, flux, [beam], ra, dec, TIMES, HERA_LOCATION, precision=2, eps=1e-12)
+    plan = eng.prepare(ants, freqs, flux, [beam], ra, dec, TIMES, HERA_LOCATION, precision=2, eps=1e-12)
+    blk = eng._evaluate_vis_chunk(slice(1, 2), slice(2, 5), plan=plan)
+    assert blk.shape == (1, full.shape[-1], 1, 1, 3)
+    np.testing.assert_allclose(blk[0, :, 0, 0, :].T, full[2:5, 1], rtol=1e-12, atol=1e-12)
+
+
+def test_f32_close_to_f64_and_no_sources_above_horizon():
+    """reference tests/test_wrapper.py:318 (rtol = atol = 1e-5 there, on O(1) visibilities)."""
+    from fftvis_b200 import AiryBeam, HERA_LOCATION, simulate_vis
+    ants = hex_ants(3)
+    ra, dec, flux = small_sky(500, FREQS)
+    beam = AiryBeam(diameter=14.0)
+    v64 = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beam, HERA_LOCATION, precision=2)
+    v32 = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beam, HERA_LOCATION, precision=1)
+    assert v32.dtype == np.complex64 and relerr(v32, v64) < 2e-5
+    # every source below the horizon -> exact zeros
+    below_dec = np.full(5, np.deg2rad(80.0))
+    out = simulate_vis(ants, flux[:5], ra[:5], below_dec, FREQS, TIMES, beam, HERA_LOCATION, precision=2)
+    assert np.all(out == 0)
+    out = simulate_vis(ants, flux[:5], ra[:5], below_dec, FREQS, TIMES, beam, HERA_LOCATION, precision=2,
+                       force_use_type3=True)
+    assert np.all(out == 0)
+
+
+def test_wrapper_errors_match_reference_strings():
+    """reference tests/test_wrapper.py:123-141, tests/test_beam_basis.py:459,476."""
+    from fftvis_b200 import GaussianBeam, HERA_LOCATION, simulate_vis
+    ants = hex_ants(2)
+    ra, dec, flux = small_sky(10, FREQS)
+    b = GaussianBeam(diameter=14.0)
+    with pytest.raises(ValueError, match="beam_idx must be provided"):
+        simulate_vis(ants, flux, ra, dec, FREQS, TIMES, [b, b], HERA_LOCATION)
+    with pytest.raises(ValueError, match="beam_idx must be length nant"):
+        simulate_vis(ants, flux, ra, dec, FREQS, TIMES, [b, b], HERA_LOCATION, beam_idx=np.zeros(3, int))
+    with pytest.raises(ValueError, match="not compatible with unpolarized"):
+        simulate_vis(ants, flux, ra, dec, FREQS, TIMES, [b], HERA_LOCATION, beam_coefs=np.ones((7, 1, 2)))
+    with pytest.raises(ValueError, match="Unsupported backend"):
+        simulate_vis(ants, flux, ra, dec, FREQS, TIMES, b, HERA_LOCATION, backend="tpu")
