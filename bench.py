@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Headline benchmark: visibility terms / second (Nsrc * Nbl * Nfreq * Ntime / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2]
+
+A "step" is one pass of the hot path (``GPUSimulationEngine.run_plan``: rotate + horizon cut, beam +
+coherency weights, batched NUFFT, epilogue) over the whole workload with every input already resident
+in HBM.  Default workload = BASELINE.json configs[1]: HERA-350-like gridded hex array (type-1 path),
+10 000 point sources, 1024 frequencies 100-200 MHz, 60 times, unpolarised Airy beam, single precision.
+At N > 1 (torchrun, one rank per GPU) every rank runs the same workload on its own block of 60 times:
+the path shards over independent (time, frequency) units with no data-path collective (weak scaling).
+
+One JSON line on stdout (rank 0).  ``e2e`` = the same metric through ``fftvis_b200.simulate_vis`` with
+host numpy buffers (planning, H2D, compute, D2H inside the timed region).  ``roofline`` = the dominant
+kernel of this library (per-launch CUDA events recorded live in the timed region).  ``cpu_baseline`` /
+``--impl reference`` = the CPU restatement of the reference pipeline (oracle/; finufft, matvis and
+pyuvdata cannot be installed offline, so the reference itself cannot run) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+START_JD = 2459845.0
+CADENCE_S = 10.0
+
+
+# --------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs)
+# --------------------------------------------------------------------------------------------
+def make_workload(name: str, nfreq=None, ntimes=None, nsrc=None, time_block: int = 0):
+    from fftvis_b200 import AiryBeam, GaussianBeam, HERA_LOCATION, synth
+    w = dict(name=name, telescope_loc=HERA_LOCATION, kwargs={})
+    if name == "cfg1":
+        nfreq, ntimes, nsrc = nfreq or 2, ntimes or 1, nsrc or 100
+        w.update(ants=synth.hex_rows((3, 4, 3)), beam=GaussianBeam(diameter=14.0), precision=2, polarized=False,
+                 desc="tests-scale: 10-antenna hex, 100 sources, 2 freqs, 1 time, Gaussian beam, f64")
+        freqs = np.linspace(100e6, 110e6, nfreq)
+        sky = synth.random_sky(nsrc, freqs, seed=42)
+    elif name == "cfg2":
+        nfreq, ntimes, nsrc = nfreq or 1024, ntimes or 60, nsrc or 10000
+        w.update(ants=synth.hera350_like(), beam=AiryBeam(diameter=14.0), precision=1, polarized=False,
+                 desc="HERA-350-like gridded hex (type-1 path), 10k GLEAM-like point sources, "
+                      "1024 freqs 100-200 MHz, 60 times, unpolarized Airy beam, single precision")
+        freqs = np.linspace(100e6, 200e6, nfreq)
+        sky = synth.random_sky(nsrc, freqs, seed=42, kind="gleam")
+    elif name == "cfg3":
+        nfreq, ntimes, nsrc = nfreq or 1024, ntimes or 60, nsrc or 100000
+        freqs = np.linspace(100e6, 200e6, nfreq)
+        w.update(ants=synth.hex_array(11), beam=synth.synthetic_uvbeam(freqs, naz=360, nza=181), precision=2,
+                 polarized=True, kwargs=dict(beam_spline_opts={"order": 1}),
+                 desc="HERA-331 polarized: synthetic UVBeam E-field on az/za grid, 4 pol products, "
+                      "100k sources, 1024 freqs, 60 times, f64")
+        sky = synth.random_sky(nsrc, freqs, seed=42, kind="gleam")
+    elif name == "cfg4":
+        nfreq, ntimes, nsrc = nfreq or 512, ntimes or 1, nsrc or 3145728
+        ants = synth.random_array(256, radius=150.0, zspan=2.0, seed=42)
+        w.update(ants=ants, beam=GaussianBeam(diameter=14.0), precision=2, polarized=False,
+                 kwargs=dict(baselines=synth.all_baselines(ants)),
+                 desc="non-gridded random 256-antenna layout (32640 baselines), 3-D type 3, diffuse sky "
+                      "(3.1M pixels, ~1.5M above horizon), 512 freqs, f64")
+        freqs = np.linspace(100e6, 200e6, nfreq)
+        sky = synth.random_sky(nsrc, freqs, seed=42, kind="diffuse")
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    t0 = START_JD + time_block * ntimes * CADENCE_S / 86400.0
+    w.update(freqs=freqs, times=t0 + np.arange(ntimes) * CADENCE_S / 86400.0, ra=sky[0], dec=sky[1],
+             fluxes=sky[2], nfreq=nfreq, ntimes=ntimes, nsrc=nsrc)
+    return w
+
+
+def n_baselines(w) -> int:
+    if "baselines" in w["kwargs"]:
+        return len(w["kwargs"]["baselines"])
+    from fftvis_b200.core import utils
+    return len(utils.get_pos_reds(w["ants"], include_autos=True))
+
+
+def terms(w, nbls, nfreq=None, ntimes=None) -> float:
+    return float(w["nsrc"]) * nbls * (nfreq or w["nfreq"]) * (ntimes or w["ntimes"])
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in Path(self.path).read_text().splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); power.append(float(p[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm (oracle = restatement of the reference pipeline)
+# --------------------------------------------------------------------------------------------
+def cpu_sample(w, nbls, budget_s: float = 15.0):
+    """Time oracle.pipeline.simulate_cpu on a bounded (time, frequency) sample of the workload with
+    every host core; returns (terms/s, description, cores, seconds)."""
+    from oracle import nufft_cpu, pipeline
+    cores = nufft_cpu.max_threads()
+    beam = w["beam"] if w["polarized"] else w["beam"].to_power()
+    base = dict(precision=w["precision"], polarized=w["polarized"], nthreads=cores, **w["kwargs"])
+
+    def run(nf, nt):
+        fs = slice(0, nf)
+        t0 = time.perf_counter()
+        pipeline.simulate_cpu(w["ants"], w["fluxes"], w["ra"], w["dec"], w["freqs"], w["times"], [beam],
+                              w["telescope_loc"], freq_slice=fs, time_slice=slice(0, nt), **base)
+        return time.perf_counter() - t0
+
+    # grow the sample geometrically until one run costs between budget/4 and budget seconds; that
+    # last run is the measurement (its one-off planning share is then small)
+    total = w["nfreq"] * w["ntimes"]
+    units = 2
+    while True:
+        nf = int(min(w["nfreq"], units))
+        nt = int(max(1, min(w["ntimes"], units // nf)))
+        dt = run(nf, nt)
+        if dt >= budget_s / 4 or nf * nt >= total:
+            break
+        units = int(min(total, max(units * 2, units * min(8.0, 0.6 * budget_s / max(dt, 1e-3)))))
+    val = terms(w, nbls, nf, nt) / dt
+    return val, f"{nf} of {w['nfreq']} freqs x {nt} of {w['ntimes']} times of the same workload, {dt:.1f} s", cores, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = make_workload(args.workload, args.nfreq, args.ntimes, args.nsrc)
+    nbls = n_baselines(w)
+    vals, secs, sample, cores = [], [], "", 1
+    for i in range(args.warmup + args.steps):
+        v, sample, cores, dt = cpu_sample(w, nbls, budget_s=args.cpu_budget)
+        if i >= args.warmup:
+            vals.append(v); secs.append(dt)
+    val = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "vis terms/sec (Nsrc*Nbl*Nfreq*Ntime/s)", "value": val, "unit": "terms/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if w["precision"] == 1 else "f64", "data": "synthetic",
+        "config": {"workload": f"{w['name']}: {w['desc']}", "nsrc": w["nsrc"], "nbls": nbls, "nfreq": w["nfreq"],
+                   "ntimes": w["ntimes"]},
+        "cpu_baseline": {"value": val, "unit": "terms/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "CPU restatement of the reference pipeline (finufft/matvis/pyuvdata unavailable offline)"},
+        "e2e": {"value": val, "unit": "terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def spread_alg_bytes(plan, n_live: float) -> float:
+    """Algorithmic bytes of ONE spread launch (DESIGN.md "spread"): NU coordinates once, strengths
+    of the batch once, and the fine grids written once."""
+    import ctypes
+    from fftvis_b200.gpu import _lib
+    r = 4 * plan.precision
+    c = 2 * r
+    P = 4 if plan.polarized else 1
+    w_, beta = ctypes.c_int(0), ctypes.c_double(0)
+    _lib.lib().fv_kernel_params(plan.eps, plan.upsample_factor, plan.precision, ctypes.byref(w_), ctypes.byref(beta))
+    nf = _lib.lib().fv_next235even(max(int(plan.upsample_factor * plan.n_modes), 2 * w_.value))
+    nb = plan.freq_batch
+    return n_live * 2 * r + nb * P * c * n_live + nb * P * c * nf * nf
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (fftvis_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import fftvis_b200
+    from fftvis_b200.gpu import GPUSimulationEngine, _lib
+
+    w = make_workload(args.workload, args.nfreq, args.ntimes, args.nsrc, time_block=rank)
+    nbls = n_baselines(w)
+    beam = w["beam"] if w["polarized"] else w["beam"].to_power()
+    eng = GPUSimulationEngine(freq_batch=args.freq_batch)
+    plan = eng.prepare(w["ants"], w["freqs"], w["fluxes"], [beam], w["ra"], w["dec"], w["times"],
+                       w["telescope_loc"], precision=w["precision"], polarized=w["polarized"], **w["kwargs"])
+    P = 4 if plan.polarized else 1
+    out = torch.zeros((plan.nf_local, plan.ntimes, P, plan.nbls),
+                      dtype=torch.complex64 if plan.precision == 1 else torch.complex128, device=plan.device)
+    nufft = eng._nufft_plan(plan.device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.run_plan(plan, out=out)
+    eng.check_source_buffer(plan)
+    barrier()
+    nufft.set_timing(True)
+    nufft.reset_timing()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib().fv_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        eng.run_plan(plan, out=out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.lib().fv_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    stages = nufft.stage_times()
+    nufft.set_timing(False)
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    total_terms = terms(w, nbls) * world * args.steps
+    value = total_terms / (ms_max * 1e-3)
+
+    # ---- end to end through the public API with host buffers ------------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    call = dict(ants=w["ants"], fluxes=w["fluxes"], ra=w["ra"], dec=w["dec"], freqs=w["freqs"], times=w["times"],
+                beam=w["beam"], telescope_loc=w["telescope_loc"], precision=w["precision"],
+                polarized=w["polarized"], **w["kwargs"])
+    del out, plan
+    torch.cuda.empty_cache()
+    fftvis_b200.simulate_vis(**call)                         # warm-up (pinned pools, cuFFT plans)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = fftvis_b200.simulate_vis(**call)
+    barrier()
+    dt = time.perf_counter() - t0
+    tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+    e2e_val = terms(w, nbls) * world * e2e_steps / float(tdt.item())
+    csz = 8 * w["precision"]
+    h2d = int(np.asarray(w["fluxes"]).size * csz + 3 * 8 * w["nsrc"] + 8 * w["nfreq"])
+    d2h = int(res.size * res.itemsize)
+
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        eng2 = GPUSimulationEngine(freq_batch=args.freq_batch)
+        plan2 = eng2.prepare(w["ants"], w["freqs"], w["fluxes"], [beam], w["ra"], w["dec"], w["times"][:1],
+                             w["telescope_loc"], precision=w["precision"], polarized=w["polarized"], **w["kwargs"])
+        # mean number of live (above-horizon) sources, for the algorithmic byte count
+        n_live = 0.5 * w["nsrc"]
+        roof = None
+        sp_ms, sp_n = stages["spread"]
+        if plan2.use_type1 and sp_n:
+            alg = spread_alg_bytes(plan2, n_live)
+            ach = alg / (sp_ms / sp_n * 1e-3) / 1e9
+            roof = {"kernel": "spread_kernel (type 1)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": alg, "avg_launch_ms": sp_ms / sp_n, "launches": sp_n}
+        stage_share = {k: {"ms": v[0], "launches": v[1], "share_of_step": v[0] / ms if ms else None}
+                       for k, v in stages.items()}
+        cpu_val, cpu_desc, cores, _ = cpu_sample(w, nbls, budget_s=args.cpu_budget)
+        line = {
+            "metric": "vis terms/sec (Nsrc*Nbl*Nfreq*Ntime/s)", "value": value, "unit": "terms/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if w["precision"] == 1 else "f64", "data": "synthetic",
+            "config": {"workload": f"{w['name']}: {w['desc']}", "nsrc": w["nsrc"], "nbls": nbls, "nfreq": w["nfreq"],
+                       "ntimes": w["ntimes"], "n_modes": plan2.n_modes, "freq_batch": plan2.freq_batch,
+                       "eps": plan2.eps, "type": 1 if plan2.use_type1 else 3,
+                       "l2": "inputs + outputs streamed per step exceed the 126 MB L2 (no explicit flush)",
+                       "sharding": "each rank simulates its own block of times; no data-path collective"},
+            "e2e": {"value": e2e_val, "unit": "terms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "fftvis_b200.simulate_vis(host numpy in, host numpy out)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "stages": stage_share,
+            "cpu_baseline": {"value": cpu_val, "unit": "terms/s", "cores": cores, "kind": "port", "sample": cpu_desc},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--nfreq", type=int, default=None)
+    ap.add_argument("--ntimes", type=int, default=None)
+    ap.add_argument("--nsrc", type=int, default=None)
+    ap.add_argument("--freq-batch", type=int, default=None)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work per cpu sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -457,9 +457,12 @@ struct fv_plan {
   double* lim_dev = nullptr;
   size_t fft_work_bytes = 0;
   size_t table_bytes = 0;
-  bool time_fft = false;
-  double fft_ms = 0.0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  bool timing = false;                       // CUDA events around every stage launch
+  double stage_ms[FV_STAGE_COUNT] = {0};
+  int64_t stage_n[FV_STAGE_COUNT] = {0};
+  struct Pending { int stage; cudaEvent_t e0, e1; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> event_pool;
   size_t max_grid_bytes = (size_t)96 << 30;   // refuse grids beyond this (B200 has 180 GB)
 };
 
@@ -504,16 +507,26 @@ static int get_fft(fv_plan* P, int prec, int dim, int64_t n1, int64_t n2, int64_
   return FV_OK;
 }
 
-static int run_fft(fv_plan* P, cufftHandle h, int prec, void* data) {
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (P->time_fft) {
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, P->stream);
+// RAII stage timer: records an event pair on the plan's stream around the launches in its scope
+struct StageScope {
+  fv_plan* P; int stage; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  static cudaEvent_t get(fv_plan* P) {
+    if (!P->event_pool.empty()) { cudaEvent_t e = P->event_pool.back(); P->event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
   }
+  StageScope(fv_plan* P_, int stage_) : P(P_), stage(stage_) {
+    if (P->timing) { e0 = get(P); e1 = get(P); cudaEventRecord(e0, P->stream); }
+  }
+  ~StageScope() {
+    if (e0) { cudaEventRecord(e1, P->stream); P->pending.push_back({stage, e0, e1}); }
+  }
+};
+
+static int run_fft(fv_plan* P, cufftHandle h, int prec, void* data) {
+  StageScope ts(P, FV_STAGE_FFT);
   cufftResult r = prec == 1 ? cufftExecC2C(h, (cufftComplex*)data, (cufftComplex*)data, CUFFT_INVERSE)
                             : cufftExecZ2Z(h, (cufftDoubleComplex*)data, (cufftDoubleComplex*)data, CUFFT_INVERSE);
   if (r != CUFFT_SUCCESS) { set_error("cufftExec failed with code " + std::to_string((int)r)); return FV_ERR_CUFFT; }
-  if (P->time_fft) { cudaEventRecord(e1, P->stream); P->pending.push_back({e0, e1}); }
   return FV_OK;
 }
 
@@ -576,6 +589,7 @@ static EpiDev make_epi(const fv_epilogue* e) {
 template <typename T>
 static int launch_spread(fv_plan* P, int dim, SpreadArgs<T>& a, int nb) {
   if (a.n_cap == 0) return FV_OK;
+  StageScope ts(P, FV_STAGE_SPREAD);
   dim3 grid(ceil_div(a.n_cap, 128), nb);
   if (dim == 2) { FV_DISPATCH_W(a.w, (spread_kernel<T, 2, WT><<<grid, 128, 0, P->stream>>>(a))); }
   else { FV_DISPATCH_W(a.w, (spread_kernel<T, 3, WT><<<grid, 128, 0, P->stream>>>(a))); }
@@ -585,6 +599,7 @@ static int launch_spread(fv_plan* P, int dim, SpreadArgs<T>& a, int nb) {
 
 template <typename T>
 static int launch_interp(fv_plan* P, int dim, InterpArgs<T>& a, int nb) {
+  StageScope ts(P, FV_STAGE_INTERP);
   dim3 grid(ceil_div(a.nk, 128), nb);
   if (dim == 2) { FV_DISPATCH_W(a.w, (interp_kernel<T, 2, WT><<<grid, 128, 0, P->stream>>>(a))); }
   else { FV_DISPATCH_W(a.w, (interp_kernel<T, 3, WT><<<grid, 128, 0, P->stream>>>(a))); }
@@ -606,7 +621,7 @@ static int nufft2d1_impl(fv_plan* P, int prec, const void* bx, const void* by, c
   if (need > P->max_grid_bytes) { set_error("type-1 batch needs " + std::to_string(need) + " bytes of grid; reduce the frequency batch"); return FV_ERR_ALLOC; }
   int rc = ensure(&P->grid, &P->grid_bytes, need);
   if (rc) return rc;
-  FV_CUDA(cudaMemsetAsync(P->grid, 0, need, P->stream));
+  { StageScope ts(P, FV_STAGE_ZERO); FV_CUDA(cudaMemsetAsync(P->grid, 0, need, P->stream)); }
   std::vector<BatchParams> bp(nb);
   for (int b = 0; b < nb; ++b) {
     bp[b] = BatchParams{};
@@ -633,6 +648,7 @@ static int nufft2d1_impl(fv_plan* P, int prec, const void* bx, const void* by, c
   if (rc) return rc;
   rc = run_fft(P, h, prec, P->grid);
   if (rc) return rc;
+  StageScope ts(P, FV_STAGE_GATHER);
   dim3 grid(ceil_div(nk, 256), nb * ntr);
   gather_modes_kernel<T><<<grid, 256, 0, P->stream>>>((const C*)P->grid, (int)nf, ntr, n_modes / 2, invphi, m1, m2, nk, make_epi(epi));
   FV_LAUNCH_CHECK();
@@ -751,7 +767,7 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
     b1 = b0 + sub;
     rc = ensure(&P->grid, &P->grid_bytes, sizeof(C) * sub * ntr * cells1); if (rc) return rc;
     rc = ensure(&P->grid2, &P->grid2_bytes, sizeof(C) * sub * ntr * cells2); if (rc) return rc;
-    FV_CUDA(cudaMemsetAsync(P->grid, 0, sizeof(C) * sub * ntr * cells1, P->stream));
+    { StageScope ts(P, FV_STAGE_ZERO); FV_CUDA(cudaMemsetAsync(P->grid, 0, sizeof(C) * sub * ntr * cells1, P->stream)); }
 
     SpreadArgs<T> a{};
     for (int d = 0; d < 3; ++d) { a.x[d] = xs[d]; a.nf[d] = (int)nf[d]; }
@@ -764,10 +780,13 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
     rc = get_invphi<T>(P, prec, nf[0], ng[0], w, beta, true, &inv1); if (rc) return rc;
     rc = get_invphi<T>(P, prec, nf[1], ng[1], w, beta, true, &inv2); if (rc) return rc;
     if (dim == 3) { rc = get_invphi<T>(P, prec, nf[2], ng[2], w, beta, true, &inv3); if (rc) return rc; }
-    dim3 g2(ceil_div((int64_t)cells2, 256), sub * ntr);
-    if (dim == 2) deconv_pad_kernel<T, 2><<<g2, 256, 0, P->stream>>>((const C*)P->grid, (C*)P->grid2, (int)nf[0], (int)nf[1], 1, (int)ng[0], (int)ng[1], 1, inv1, inv2, inv3);
-    else deconv_pad_kernel<T, 3><<<g2, 256, 0, P->stream>>>((const C*)P->grid, (C*)P->grid2, (int)nf[0], (int)nf[1], (int)nf[2], (int)ng[0], (int)ng[1], (int)ng[2], inv1, inv2, inv3);
-    FV_LAUNCH_CHECK();
+    {
+      StageScope ts(P, FV_STAGE_DECONV);
+      dim3 g2(ceil_div((int64_t)cells2, 256), sub * ntr);
+      if (dim == 2) deconv_pad_kernel<T, 2><<<g2, 256, 0, P->stream>>>((const C*)P->grid, (C*)P->grid2, (int)nf[0], (int)nf[1], 1, (int)ng[0], (int)ng[1], 1, inv1, inv2, inv3);
+      else deconv_pad_kernel<T, 3><<<g2, 256, 0, P->stream>>>((const C*)P->grid, (C*)P->grid2, (int)nf[0], (int)nf[1], (int)nf[2], (int)ng[0], (int)ng[1], (int)ng[2], inv1, inv2, inv3);
+      FV_LAUNCH_CHECK();
+    }
     cufftHandle h;
     rc = get_fft(P, prec, dim, ng[0], ng[1], ng[2], (int64_t)sub * ntr, &h); if (rc) return rc;
     rc = run_fft(P, h, prec, P->grid2); if (rc) return rc;
@@ -815,7 +834,8 @@ extern "C" int fv_plan_destroy(fv_plan* P) {
   if (!P) return FV_OK;
   for (auto& kv : P->ffts) cufftDestroy(kv.second);
   for (auto& kv : P->invphi) cudaFree(kv.second);
-  for (auto& ev : P->pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (auto& ev : P->pending) { cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1); }
+  for (auto& ev : P->event_pool) cudaEventDestroy(ev);
   if (P->grid) cudaFree(P->grid);
   if (P->grid2) cudaFree(P->grid2);
   if (P->bp_dev) cudaFree(P->bp_dev);
@@ -824,23 +844,42 @@ extern "C" int fv_plan_destroy(fv_plan* P) {
   return FV_OK;
 }
 
-extern "C" int fv_plan_set_fft_timing(fv_plan* P, int enable) {
+namespace fv {
+static int drain_timing(fv_plan* P) {
+  for (auto& ev : P->pending) {
+    FV_CUDA(cudaEventSynchronize(ev.e1));
+    float ms = 0;
+    FV_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+    P->stage_ms[ev.stage] += ms;
+    P->stage_n[ev.stage] += 1;
+    P->event_pool.push_back(ev.e0); P->event_pool.push_back(ev.e1);
+  }
+  P->pending.clear();
+  return FV_OK;
+}
+}  // namespace fv
+
+extern "C" int fv_plan_set_timing(fv_plan* P, int enable) {
   FV_REQUIRE(P, "null plan");
-  P->time_fft = enable != 0;
+  P->timing = enable != 0;
   return FV_OK;
 }
 
-extern "C" int fv_plan_fft_ms(fv_plan* P, double* ms_host) {
-  FV_REQUIRE(P && ms_host, "null pointer");
-  for (auto& ev : P->pending) {
-    FV_CUDA(cudaEventSynchronize(ev.second));
-    float ms = 0;
-    FV_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
-    P->fft_ms += ms;
-    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
-  }
-  P->pending.clear();
-  *ms_host = P->fft_ms;
+extern "C" int fv_plan_reset_timing(fv_plan* P) {
+  FV_REQUIRE(P, "null plan");
+  int rc = fv::drain_timing(P);
+  if (rc) return rc;
+  for (int i = 0; i < FV_STAGE_COUNT; ++i) { P->stage_ms[i] = 0.0; P->stage_n[i] = 0; }
+  return FV_OK;
+}
+
+extern "C" int fv_plan_stage_ms(fv_plan* P, int stage, double* ms_host, int64_t* count_host) {
+  FV_REQUIRE(P && ms_host && count_host, "null pointer");
+  FV_REQUIRE(stage >= 0 && stage < FV_STAGE_COUNT, "unknown stage");
+  int rc = fv::drain_timing(P);
+  if (rc) return rc;
+  *ms_host = P->stage_ms[stage];
+  *count_host = P->stage_n[stage];
   return FV_OK;
 }
 

@@ -52,8 +52,9 @@ _SIGNATURES = {
     "fv_coherency": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "fv_plan_create": (c_int, [POINTER(c_void_p), c_void_p]),
     "fv_plan_destroy": (c_int, [c_void_p]),
-    "fv_plan_set_fft_timing": (c_int, [c_void_p, c_int]),
-    "fv_plan_fft_ms": (c_int, [c_void_p, POINTER(c_double)]),
+    "fv_plan_set_timing": (c_int, [c_void_p, c_int]),
+    "fv_plan_reset_timing": (c_int, [c_void_p]),
+    "fv_plan_stage_ms": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int64)]),
     "fv_plan_bytes": (c_int64, [c_void_p]),
     "fv_nufft2d1": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                             POINTER(c_double), c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
@@ -73,6 +74,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
+STAGES = ("zero", "spread", "fft", "gather", "deconv", "interp")
 
 
 @lru_cache(maxsize=1)

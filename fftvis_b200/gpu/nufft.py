@@ -45,13 +45,20 @@ class NufftPlan:
     def handle(self):
         return self._h
 
-    def set_fft_timing(self, enable: bool):
-        _lib.check(_lib.lib().fv_plan_set_fft_timing(self._h, int(enable)))
+    def set_timing(self, enable: bool):
+        _lib.check(_lib.lib().fv_plan_set_timing(self._h, int(enable)))
 
-    def fft_ms(self) -> float:
-        ms = ctypes.c_double(0)
-        _lib.check(_lib.lib().fv_plan_fft_ms(self._h, ctypes.byref(ms)))
-        return ms.value
+    def reset_timing(self):
+        _lib.check(_lib.lib().fv_plan_reset_timing(self._h))
+
+    def stage_times(self) -> dict:
+        """{stage: (milliseconds, launches)} since the last reset (synchronises)."""
+        out = {}
+        for i, name in enumerate(_lib.STAGES):
+            ms, cnt = ctypes.c_double(0), ctypes.c_int64(0)
+            _lib.check(_lib.lib().fv_plan_stage_ms(self._h, i, ctypes.byref(ms), ctypes.byref(cnt)))
+            out[name] = (ms.value, cnt.value)
+        return out
 
     def bytes(self) -> int:
         return int(_lib.lib().fv_plan_bytes(self._h))
@@ -139,12 +146,13 @@ def gpu_nufft2d_type1(x, y, weights, n_modes, index, eps, upsample_factor=2, n_t
     prec = _prec_of(weights)
     rdt, cdt = _RDT[prec], _CDT[prec]
     index = np.asarray(index)
-    half = (int(n_modes) - 1) // 2 if n_modes % 2 else int(n_modes) // 2
+    n_modes = int(n_modes)
     m = index[:2].astype(np.int64)
-    # Python-style wrap of out-of-range / negative indices into signed mode numbers
-    m = np.where(m > half, m - int(n_modes), m)
-    if np.any(np.abs(m) > int(n_modes) // 2):
-        raise IndexError("mode index out of range for n_modes")
+    if np.any(m >= n_modes) or np.any(m < -n_modes):     # numpy fancy-index semantics of cpu/nufft.py:175
+        raise IndexError(f"index out of bounds for axis with size {n_modes}")
+    # FFT-ordered array position (negative = from the end) -> signed mode number
+    pos = np.where(m < 0, m + n_modes, m)
+    m = np.where(pos > (n_modes - 1) // 2, pos - n_modes, pos)
     W = _to_dev(np.atleast_2d(weights), cdt).unsqueeze(0).contiguous()
     n = W.shape[-1]
     bx, by = _to_dev(x, rdt), _to_dev(y, rdt)

@@ -118,10 +118,23 @@ int fv_coherency(int prec, int mode, const void* beam_i, const void* beam_j,
 typedef struct fv_plan fv_plan; /* opaque: cuFFT plan cache + work grids, one per GPU/stream */
 int fv_plan_create(fv_plan** plan, void* stream);
 int fv_plan_destroy(fv_plan* plan);
-/* cumulative device time (ms) spent inside cuFFT exec calls when timing is enabled (north_star:
- * "the inner uniform FFT ... is timed separately"); enable=1 inserts events around every exec */
-int fv_plan_set_fft_timing(fv_plan* plan, int enable);
-int fv_plan_fft_ms(fv_plan* plan, double* ms_host);
+/* per-stage device time: with timing enabled every stage launch inside fv_nufft2d1 / fv_nufft3 is
+ * bracketed by a CUDA event pair on the plan's stream (north_star: "the inner uniform FFT ... is
+ * timed separately"; bench.py's roofline block uses the spread / interp entries).
+ * fv_plan_stage_ms returns the cumulative milliseconds and launch count of one stage since the
+ * last reset (it synchronises on the outstanding events). */
+typedef enum {
+  FV_STAGE_ZERO = 0,    /* clearing the fine grid */
+  FV_STAGE_SPREAD = 1,  /* spread kernel (type 1 and type 3 step 1) */
+  FV_STAGE_FFT = 2,     /* cuFFT exec */
+  FV_STAGE_GATHER = 3,  /* type 1 deconvolve + mode gather + epilogue */
+  FV_STAGE_DECONV = 4,  /* type 3 deconvolve + zero-pad */
+  FV_STAGE_INTERP = 5,  /* type 3 interpolation + post-phase + epilogue */
+  FV_STAGE_COUNT = 6
+} fv_stage;
+int fv_plan_set_timing(fv_plan* plan, int enable);
+int fv_plan_reset_timing(fv_plan* plan);
+int fv_plan_stage_ms(fv_plan* plan, int stage, double* ms_host, int64_t* count_host);
 /* bytes of device memory the plan currently holds (grids + cuFFT work areas) */
 int64_t fv_plan_bytes(fv_plan* plan);
 

@@ -61,7 +61,13 @@ def test_type3_vs_oracle(prec, eps, dim, upsamp):
     want = nc.direct_sum(xs[0], xs[1], xs[2] if dim == 3 else None, c, ss[0], ss[1],
                          ss[2] if dim == 3 else None)
     floor = 1e-9 if upsamp == 1.25 else 0.0
-    tol = max(10 * eps, floor) if prec == 2 else 3e-5
+    if prec == 2:
+        tol = max(10 * eps, floor)
+    else:
+        # fp32: the yardstick is the CPU restatement's own fp32 error on the same inputs (sigma = 1.25
+        # amplifies fp32 rounding through the larger 1/phihat deconvolution factors)
+        cpu = nc.nufft_type3(xs, c, ss, eps, upsampfac=upsamp)
+        tol = max(3e-5, 3 * relerr(cpu, want))
     assert got.shape == want.shape
     assert relerr(got, want) < tol
 
