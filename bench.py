@@ -208,8 +208,10 @@ def run_reference(args):
 # GPU arm
 # --------------------------------------------------------------------------------------------
 def spread_alg_bytes(plan, n_live: float) -> float:
-    """Algorithmic bytes of ONE spread launch (DESIGN.md "spread"): NU coordinates once, strengths
-    of the batch once, and the fine grids written once."""
+    """Algorithmic bytes of ONE launch of the type-1 spreader (the per-unit
+    figure of SURVEY.md section 8(d) restricted to this kernel, times the frequencies of a batch):
+    NU coordinates and strengths read once, the fine grid written once.  The fused kernel keeps the
+    grid in shared memory, so its real DRAM traffic (``traffic``) is far below this figure."""
     import ctypes
     from fftvis_b200.gpu import _lib
     r = 4 * plan.precision
@@ -219,7 +221,7 @@ def spread_alg_bytes(plan, n_live: float) -> float:
     _lib.lib().fv_kernel_params(plan.eps, plan.upsample_factor, plan.precision, ctypes.byref(w_), ctypes.byref(beta))
     nf = _lib.lib().fv_next235even(max(int(plan.upsample_factor * plan.n_modes), 2 * w_.value))
     nb = plan.freq_batch
-    return n_live * 2 * r + nb * P * c * n_live + nb * P * c * nf * nf
+    return nb * (n_live * (2 * r + P * c) + P * c * nf * nf)
 
 
 def run_gpu(args):
@@ -241,7 +243,7 @@ def run_gpu(args):
     w = make_workload(args.workload, args.nfreq, args.ntimes, args.nsrc, time_block=rank)
     nbls = n_baselines(w)
     beam = w["beam"] if w["polarized"] else w["beam"].to_power()
-    eng = GPUSimulationEngine(freq_batch=args.freq_batch)
+    eng = GPUSimulationEngine(freq_batch=args.freq_batch, type1_method=args.type1_method)
     plan = eng.prepare(w["ants"], w["freqs"], w["fluxes"], [beam], w["ra"], w["dec"], w["times"],
                        w["telescope_loc"], precision=w["precision"], polarized=w["polarized"], **w["kwargs"])
     P = 4 if plan.polarized else 1
@@ -312,7 +314,7 @@ def run_gpu(args):
             peaks = json.loads(pk.read_text())
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        eng2 = GPUSimulationEngine(freq_batch=args.freq_batch)
+        eng2 = GPUSimulationEngine(freq_batch=args.freq_batch, type1_method=args.type1_method)
         plan2 = eng2.prepare(w["ants"], w["freqs"], w["fluxes"], [beam], w["ra"], w["dec"], w["times"][:1],
                              w["telescope_loc"], precision=w["precision"], polarized=w["polarized"], **w["kwargs"])
         # mean number of live (above-horizon) sources, for the algorithmic byte count
@@ -322,7 +324,9 @@ def run_gpu(args):
         if plan2.use_type1 and sp_n:
             alg = spread_alg_bytes(plan2, n_live)
             ach = alg / (sp_ms / sp_n * 1e-3) / 1e9
-            roof = {"kernel": "spread_kernel (type 1)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+            kname = ("t1_spread_fftx_kernel (fused spread + FFT-x, grid in shared memory)"
+                     if eng.type1_method == "fused" else "spread_kernel (type 1, global grid)")
+            roof = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                     "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "alg_bytes_per_launch": alg, "avg_launch_ms": sp_ms / sp_n, "launches": sp_n}
         stage_share = {k: {"ms": v[0], "launches": v[1], "share_of_step": v[0] / ms if ms else None}
@@ -335,7 +339,7 @@ def run_gpu(args):
             "dtype": "f32" if w["precision"] == 1 else "f64", "data": "synthetic",
             "config": {"workload": f"{w['name']}: {w['desc']}", "nsrc": w["nsrc"], "nbls": nbls, "nfreq": w["nfreq"],
                        "ntimes": w["ntimes"], "n_modes": plan2.n_modes, "freq_batch": plan2.freq_batch,
-                       "eps": plan2.eps, "type": 1 if plan2.use_type1 else 3,
+                       "eps": plan2.eps, "type": 1 if plan2.use_type1 else 3, "type1_method": args.type1_method,
                        "l2": "inputs + outputs streamed per step exceed the 126 MB L2 (no explicit flush)",
                        "sharding": "each rank simulates its own block of times; no data-path collective"},
             "e2e": {"value": e2e_val, "unit": "terms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -363,6 +367,7 @@ def main():
     ap.add_argument("--ntimes", type=int, default=None)
     ap.add_argument("--nsrc", type=int, default=None)
     ap.add_argument("--freq-batch", type=int, default=None)
+    ap.add_argument("--type1-method", default="fused", choices=["fused", "cufft"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work per cpu sample")
     args = ap.parse_args()

@@ -31,7 +31,7 @@ def _stale(target: Path, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     objdir = HERE / "_obj"
     objdir.mkdir(exist_ok=True)
-    headers = [HERE / "common.cuh", ROOT / "include" / "fftvis_b200.h"]
+    headers = [*sorted(HERE.glob("*.cuh")), ROOT / "include" / "fftvis_b200.h"]
     jobs = []
     for src in SOURCES:
         obj = objdir / (src[:-3] + ".o")

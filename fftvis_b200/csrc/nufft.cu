@@ -444,6 +444,8 @@ basis_contract_kernel(const cplx_t<T>* __restrict__ vkl, int64_t nk, const cplx_
 
 }  // namespace fv
 
+#include "type1_fused.cuh"
+
 // ================================================================================================
 // plan object
 // ================================================================================================
@@ -464,6 +466,25 @@ struct fv_plan {
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> event_pool;
   size_t max_grid_bytes = (size_t)96 << 30;   // refuse grids beyond this (B200 has 180 GB)
+  // shared-memory FFT plans of the fused type-1 path, keyed by (prec, nf)
+  struct SmemFft { fv::FftStages st; void* tw = nullptr; std::vector<int> pos; };
+  std::map<std::pair<int, int64_t>, SmemFft> smem_ffts;
+  void* tbuf = nullptr; size_t tbuf_bytes = 0;   // half-transformed array T of the fused type-1 path
+  void* prep = nullptr; size_t prep_bytes = 0;   // folded NU points (ix0, iy0, zx, zy) of the current batch
+  int t1_rows = 0;                               // strip height override (0 = automatic)
+  int t1_cols = 0;                               // columns per CTA override (0 = automatic)
+};
+
+// baselines of one beam pair as integer modes, bucketed by first mode number (fused type-1 path)
+struct fv_modeset {
+  std::vector<int32_t> m1, m2;
+  int n_modes = 0;
+  struct Tables {
+    int ncols = 0;
+    int32_t* col_pos = nullptr; int32_t* col_off = nullptr; int32_t* s_k = nullptr; int32_t* s_pos = nullptr;
+    void* s_scale = nullptr;
+  };
+  std::map<std::tuple<int, int64_t, int, double>, Tables> tables;   // (prec, nf, w, beta)
 };
 
 namespace fv {
@@ -655,6 +676,245 @@ static int nufft2d1_impl(fv_plan* P, int prec, const void* bx, const void* by, c
   return FV_OK;
 }
 
+
+// ---- type 1, fused shared-memory path ----------------------------------------------------------
+static int get_smem_fft(fv_plan* P, int prec, int64_t nf, fv_plan::SmemFft** out) {
+  auto key = std::make_pair(prec, nf);
+  auto it = P->smem_ffts.find(key);
+  if (it != P->smem_ffts.end()) { *out = &it->second; return FV_OK; }
+  fv_plan::SmemFft f;
+  // factor order: 4s, then a 2, then 5s, then 3s (odd radices last keep the late, short-stride
+  // stages free of shared-memory bank conflicts)
+  int64_t n = nf;
+  std::vector<int> rad;
+  while (n % 4 == 0) { rad.push_back(4); n /= 4; }
+  while (n % 2 == 0) { rad.push_back(2); n /= 2; }
+  while (n % 5 == 0) { rad.push_back(5); n /= 5; }
+  while (n % 3 == 0) { rad.push_back(3); n /= 3; }
+  if (n != 1 || (int)rad.size() > T1_MAX_STAGES || nf >= 65536) {
+    set_error("fused type-1 path needs a 2-3-5-smooth grid size below 65536");
+    return FV_ERR_UNSUPPORTED;
+  }
+  f.st.nstage = (int)rad.size();
+  int64_t cur = nf;
+  for (int i = 0; i < f.st.nstage; ++i) {
+    f.st.radix[i] = rad[i];
+    const int64_t m = cur / rad[i];
+    f.st.inv_m[i] = m == 1 ? 0u : (unsigned)(((1ull << 32) / (unsigned long long)m) + 1ull);
+    cur = m;
+  }
+  // digit-reversed output positions
+  f.pos.resize(nf);
+  for (int64_t k = 0; k < nf; ++k) {
+    int64_t kk = k, wgt = nf, p = 0;
+    for (int i = 0; i < f.st.nstage; ++i) { wgt /= rad[i]; p += (kk % rad[i]) * wgt; kk /= rad[i]; }
+    f.pos[k] = (int)p;
+  }
+  // per-stage twiddle tables, laid out so that consecutive butterflies read consecutive words
+  const size_t csz = prec == 1 ? sizeof(float2) : sizeof(double2);
+  std::vector<double> twr, twi;
+  cur = nf;
+  for (int i = 0; i < f.st.nstage; ++i) {
+    const int64_t r = rad[i], m = cur / r;
+    f.st.tw_off[i] = (int)twr.size();
+    if (m > 1)
+      for (int64_t q = 1; q < r; ++q)
+        for (int64_t j = 0; j < m; ++j) {
+          const double ang = 2.0 * M_PI * (double)((j * q) % cur) / (double)cur;
+          twr.push_back(cos(ang)); twi.push_back(sin(ang));
+        }
+    cur = m;
+  }
+  if (twr.empty()) { twr.push_back(1.0); twi.push_back(0.0); }
+  f.st.tw_len = (int)twr.size();
+  std::vector<unsigned char> host(csz * twr.size());
+  for (size_t t = 0; t < twr.size(); ++t) {
+    if (prec == 1) ((float2*)host.data())[t] = make_float2((float)twr[t], (float)twi[t]);
+    else ((double2*)host.data())[t] = make_double2(twr[t], twi[t]);
+  }
+  FV_CUDA(cudaMalloc(&f.tw, host.size()));
+  FV_CUDA(cudaMemcpyAsync(f.tw, host.data(), host.size(), cudaMemcpyHostToDevice, P->stream));
+  FV_CUDA(cudaStreamSynchronize(P->stream));
+  P->table_bytes += host.size();
+  auto res = P->smem_ffts.emplace(key, std::move(f));
+  *out = &res.first->second;
+  return FV_OK;
+}
+
+template <typename T>
+static int get_modeset_tables(fv_plan* P, fv_modeset* M, int prec, int64_t nf, int w, double beta,
+                              const fv_plan::SmemFft& F, fv_modeset::Tables** out) {
+  auto key = std::make_tuple(prec, nf, w, beta);
+  auto it = M->tables.find(key);
+  if (it != M->tables.end()) { *out = &it->second; return FV_OK; }
+  const int64_t nk = (int64_t)M->m1.size();
+  const int half = M->n_modes / 2;
+  Quad Q = make_quad(w, beta);
+  std::vector<double> ph = kernel_ft_series(nf, Q);
+  // columns = sorted unique first mode numbers
+  std::vector<int32_t> order(nk);
+  for (int64_t k = 0; k < nk; ++k) order[k] = (int32_t)k;
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return M->m1[a] < M->m1[b]; });
+  std::vector<int32_t> col_pos, col_off, s_k(nk), s_pos(nk);
+  std::vector<T> s_scale(nk);
+  for (int64_t i = 0; i < nk; ++i) {
+    const int32_t k = order[i];
+    const int a1 = M->m1[k], a2 = M->m2[k];
+    if (i == 0 || a1 != M->m1[order[i - 1]]) {
+      col_off.push_back((int32_t)i);
+      col_pos.push_back(F.pos[a1 < 0 ? a1 + nf : a1]);
+    }
+    s_k[i] = k;
+    s_pos[i] = F.pos[a2 < 0 ? a2 + nf : a2];
+    s_scale[i] = (T)(1.0 / (ph[abs(a1)] * ph[abs(a2)]));
+    (void)half;
+  }
+  col_off.push_back((int32_t)nk);
+  fv_modeset::Tables t;
+  t.ncols = (int)col_pos.size();
+  auto up = [&](const void* src, size_t bytes, void** dst) -> int {
+    FV_CUDA(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
+    if (bytes) FV_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, P->stream));
+    return FV_OK;
+  };
+  int rc;
+  if ((rc = up(col_pos.data(), col_pos.size() * 4, (void**)&t.col_pos))) return rc;
+  if ((rc = up(col_off.data(), col_off.size() * 4, (void**)&t.col_off))) return rc;
+  if ((rc = up(s_k.data(), s_k.size() * 4, (void**)&t.s_k))) return rc;
+  if ((rc = up(s_pos.data(), s_pos.size() * 4, (void**)&t.s_pos))) return rc;
+  if ((rc = up(s_scale.data(), s_scale.size() * sizeof(T), &t.s_scale))) return rc;
+  FV_CUDA(cudaStreamSynchronize(P->stream));
+  auto res = M->tables.emplace(key, t);
+  *out = &res.first->second;
+  return FV_OK;
+}
+
+template <typename T, int WT>
+static int launch_t1_spread(fv_plan* P, T1SpreadArgs<T>& a, dim3 grid, int threads, size_t smem) {
+  auto kern = t1_spread_fftx_kernel<T, WT>;
+  FV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, threads, smem, P->stream>>>(a);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+template <typename T>
+static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void* by, const int32_t* n_dev,
+                               int64_t n_cap, const double* scale, int nb, int ntr, const void* W,
+                               fv_modeset* M, double eps, double upsampfac, const fv_epilogue* epi) {
+  using C = cplx_t<T>;
+  int w; double beta;
+  kernel_params(eps, upsampfac, prec, &w, &beta);
+  const int n_modes = M->n_modes;
+  const int64_t nf = next235even(std::max<int64_t>((int64_t)(upsampfac * n_modes), 2 * w));
+  fv_plan::SmemFft* F;
+  int rc = get_smem_fft(P, prec, nf, &F);
+  if (rc) return rc;
+  fv_modeset::Tables* tab;
+  rc = get_modeset_tables<T>(P, M, prec, nf, w, beta, *F, &tab);
+  if (rc) return rc;
+  const int ncols = tab->ncols;
+  const int pitch = (int)nf + 1;
+  const size_t tneed = sizeof(C) * (size_t)nb * ntr * ncols * nf;
+  rc = ensure(&P->tbuf, &P->tbuf_bytes, tneed);
+  if (rc) return rc;
+  std::vector<BatchParams> bp(nb);
+  for (int b = 0; b < nb; ++b) {
+    bp[b] = BatchParams{};
+    bp[b].smul = scale[b]; bp[b].tmul = 1.0;
+    for (int d = 0; d < 3; ++d) bp[b].invgam[d] = 1.0;
+  }
+  rc = upload_bp(P, bp);
+  if (rc) return rc;
+
+  // ---- pass 1: spread + FFT along x ------------------------------------------------------------
+  const int wmax = (w == 7 || w == 9 || w == 11 || w == 13 || w == 14) ? w : kMaxW;
+  const size_t row_bytes = sizeof(C) * pitch;
+  const size_t smem_max = 227 * 1024 - 1024;
+  // strip height R and CTA size: whole grid in one CTA when it fits; otherwise 16 rows x 512 threads
+  // (one row per warp) if that fits, else 8 rows x 256 threads
+  // strip height R: the whole grid when it fits one CTA, else as many rows as shared memory holds
+  // (<= 32); one warp per strip row (256..768 threads): the row FFTs are warp tasks
+  auto thr_for = [](int64_t rows) { return (int)std::min<int64_t>(768, std::max<int64_t>(256, 32 * rows)); };
+  int R;
+  if (P->t1_rows > 0) R = (int)std::min<int64_t>(P->t1_rows, nf);
+  else if (t1_spread_fixed_smem<T>((int)nf, wmax, thr_for(nf)) + row_bytes * nf <= 200 * 1024) R = (int)nf;
+  else {
+    R = 32;
+    while (R > 1 && t1_spread_fixed_smem<T>((int)nf, wmax, thr_for(R)) + row_bytes * R > smem_max) --R;
+    if (R > 8) R -= R % 8;
+  }
+  int threads = thr_for(R);
+  size_t fixed1 = t1_spread_fixed_smem<T>((int)nf, wmax, threads);
+  while (R > 1 && fixed1 + row_bytes * R > smem_max) --R;
+  if (fixed1 + row_bytes * R > smem_max) { set_error("fine-grid row does not fit shared memory: use the cuFFT type-1 path"); return FV_ERR_UNSUPPORTED; }
+  // fold every (frequency, source) point once
+  const size_t per = (size_t)nb * n_cap;
+  rc = ensure(&P->prep, &P->prep_bytes, per * (2 * sizeof(int32_t) + 2 * sizeof(T)));
+  if (rc) return rc;
+  int32_t* ix0 = (int32_t*)P->prep;
+  int32_t* iy0 = ix0 + per;
+  T* zx = (T*)(iy0 + per);
+  T* zy = zx + per;
+  {
+    StageScope ts(P, FV_STAGE_ZERO);
+    dim3 grid(ceil_div(n_cap, 256), nb);
+    t1_prep_kernel<T><<<grid, 256, 0, P->stream>>>((const T*)bx, (const T*)by, n_dev, n_cap, P->bp_dev, (int)nf, w, ix0, iy0, zx, zy);
+    FV_LAUNCH_CHECK();
+  }
+  T1SpreadArgs<T> a{};
+  a.n_dev = n_dev; a.n_cap = n_cap; a.ix0 = ix0; a.iy0 = iy0; a.zx = zx; a.zy = zy;
+  a.nf = (int)nf; a.R = R; a.pitch = pitch; a.w = w;
+  a.beta = (T)beta; a.c = (T)(4.0 / ((double)w * w)); a.halfw = (T)(w / 2.0);
+  a.ntr = ntr; a.W = (const C*)W; a.tw = (const C*)F->tw; a.st = F->st;
+  a.ncols = ncols; a.col_pos = tab->col_pos; a.Tbuf = (C*)P->tbuf;
+  {
+    StageScope ts(P, FV_STAGE_SPREAD);
+    dim3 grid(ceil_div(nf, R), nb * ntr);
+    const size_t smem = fixed1 + row_bytes * R;
+    static const bool dbg = getenv("FV_DEBUG") != nullptr;
+    static long long* dbg_dev = nullptr;
+    if (dbg) {
+      if (!dbg_dev) { cudaMalloc((void**)&dbg_dev, 96); }
+      cudaMemsetAsync(dbg_dev, 0, 96, P->stream);
+      a.dbg = dbg_dev;
+    }
+    if (dbg) fprintf(stderr, "[fv] t1 fused: nf=%lld w=%d ncols=%d R=%d threads=%d smem=%zu grid=(%u,%u)\n",
+                     (long long)nf, w, ncols, R, threads, smem, grid.x, grid.y);
+    FV_DISPATCH_W(w, (rc = launch_t1_spread<T, WT>(P, a, grid, threads, smem)));
+    if (rc) return rc;
+    if (dbg) {
+      long long hcyc[12];
+      cudaMemcpyAsync(hcyc, dbg_dev, 96, cudaMemcpyDeviceToHost, P->stream);
+      cudaStreamSynchronize(P->stream);
+      const double nw = 8.0 * (threads / 32);
+      fprintf(stderr, "[fv] t1 pass-1 cycles/warp: zero %.0f scan %.0f fill %.0f spread %.0f fft %.0f fftwait %.0f write %.0f hits/strip %.0f passA %.0f passB %.0f hits/warp %.1f\n",
+              hcyc[0] / nw, hcyc[1] / nw, hcyc[2] / nw, hcyc[3] / nw, hcyc[4] / nw, hcyc[5] / nw, hcyc[6] / nw, hcyc[7] / nw, hcyc[8] / nw, hcyc[9] / nw, hcyc[10] / nw);
+    }
+  }
+  // ---- pass 2: FFT along y + deconvolve + gather -----------------------------------------------
+  const size_t fixed2 = sizeof(C) * nf;
+  int cpc = P->t1_cols > 0 ? P->t1_cols : (int)std::max<size_t>(1, (100 * 1024 - std::min<size_t>(fixed2, 99 * 1024)) / row_bytes);
+  cpc = std::min(cpc, 16);
+  if (cpc >= 8) cpc -= cpc % 8;
+  cpc = std::min(cpc, ncols);
+  while (cpc > 1 && fixed2 + row_bytes * cpc > smem_max) --cpc;
+  T1GatherArgs<T> g{};
+  g.Tbuf = (const C*)P->tbuf; g.nf = (int)nf; g.pitch = pitch; g.ncols = ncols; g.cols_per_cta = cpc; g.ntr = ntr;
+  g.tw = (const C*)F->tw; g.st = F->st; g.col_off = tab->col_off; g.s_k = tab->s_k; g.s_pos = tab->s_pos;
+  g.s_scale = (const T*)tab->s_scale; g.epi = make_epi(epi);
+  {
+    StageScope ts(P, FV_STAGE_GATHER);
+    auto kern = t1_ffty_gather_kernel<T>;
+    const size_t smem = fixed2 + row_bytes * cpc;
+    FV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(ncols, cpc), nb * ntr);
+    kern<<<grid, T1_THREADS, smem, P->stream>>>(g);
+    FV_LAUNCH_CHECK();
+  }
+  return FV_OK;
+}
+
 // ---- type 3 ------------------------------------------------------------------------------------
 static void arraywidcen(double lo, double hi, double* w, double* c) {
   *w = (hi - lo) / 2.0; *c = (hi + lo) / 2.0;
@@ -840,6 +1100,9 @@ extern "C" int fv_plan_destroy(fv_plan* P) {
   if (P->grid2) cudaFree(P->grid2);
   if (P->bp_dev) cudaFree(P->bp_dev);
   if (P->lim_dev) cudaFree(P->lim_dev);
+  if (P->tbuf) cudaFree(P->tbuf);
+  if (P->prep) cudaFree(P->prep);
+  for (auto& kv : P->smem_ffts) cudaFree(kv.second.tw);
   delete P;
   return FV_OK;
 }
@@ -885,7 +1148,7 @@ extern "C" int fv_plan_stage_ms(fv_plan* P, int stage, double* ms_host, int64_t*
 
 extern "C" int64_t fv_plan_bytes(fv_plan* P) {
   if (!P) return 0;
-  return (int64_t)(P->grid_bytes + P->grid2_bytes + P->fft_work_bytes + P->table_bytes);
+  return (int64_t)(P->grid_bytes + P->grid2_bytes + P->tbuf_bytes + P->prep_bytes + P->fft_work_bytes + P->table_bytes);
 }
 
 extern "C" int fv_nufft2d1(fv_plan* plan, int prec, const void* bx, const void* by, const int32_t* n_dev,
@@ -901,6 +1164,55 @@ extern "C" int fv_nufft2d1(fv_plan* plan, int prec, const void* bx, const void* 
   if (nb == 0 || nk == 0) return FV_OK;
   if (prec == 1) return fv::nufft2d1_impl<float>(plan, prec, bx, by, n_dev, n_cap, scale_host, nb, ntr, W, n_modes, m1, m2, nk, eps, upsampfac, epi_host);
   return fv::nufft2d1_impl<double>(plan, prec, bx, by, n_dev, n_cap, scale_host, nb, ntr, W, n_modes, m1, m2, nk, eps, upsampfac, epi_host);
+}
+
+
+extern "C" int fv_modeset_create(fv_modeset** ms, const int32_t* m1_host, const int32_t* m2_host, int64_t nk,
+                                 int n_modes) {
+  FV_REQUIRE(ms && (nk == 0 || (m1_host && m2_host)), "null pointer");
+  FV_REQUIRE(n_modes >= 1 && nk >= 0, "bad n_modes / nk");
+  const int half = n_modes / 2;
+  for (int64_t k = 0; k < nk; ++k)
+    FV_REQUIRE(abs(m1_host[k]) <= half && abs(m2_host[k]) <= half, "mode number outside [-n_modes/2, n_modes/2]");
+  fv_modeset* M = new fv_modeset();
+  M->m1.assign(m1_host, m1_host + nk);
+  M->m2.assign(m2_host, m2_host + nk);
+  M->n_modes = n_modes;
+  *ms = M;
+  return FV_OK;
+}
+
+extern "C" int fv_modeset_destroy(fv_modeset* M) {
+  if (!M) return FV_OK;
+  for (auto& kv : M->tables) {
+    cudaFree(kv.second.col_pos); cudaFree(kv.second.col_off); cudaFree(kv.second.s_k);
+    cudaFree(kv.second.s_pos); cudaFree(kv.second.s_scale);
+  }
+  delete M;
+  return FV_OK;
+}
+
+extern "C" int fv_plan_set_option(fv_plan* P, const char* name, int64_t value) {
+  FV_REQUIRE(P && name, "null pointer");
+  const std::string n(name);
+  if (n == "t1_rows") P->t1_rows = (int)value;
+  else if (n == "t1_cols") P->t1_cols = (int)value;
+  else if (n == "max_grid_bytes") P->max_grid_bytes = (size_t)value;
+  else { fv::set_error("unknown option " + n); return FV_ERR_INVALID; }
+  return FV_OK;
+}
+
+extern "C" int fv_nufft2d1_fused(fv_plan* plan, int prec, const void* bx, const void* by, const int32_t* n_dev,
+                                 int64_t n_cap, const double* scale_host, int nb, int ntr, const void* W,
+                                 fv_modeset* modes, double eps, double upsampfac, const fv_epilogue* epi_host) {
+  FV_REQUIRE(plan && bx && by && n_dev && scale_host && W && modes && epi_host && epi_host->out, "null pointer");
+  FV_REQUIRE(prec == 1 || prec == 2, "prec must be 1 or 2");
+  FV_REQUIRE(ntr >= 1 && ntr <= 4, "ntr must be 1..4");
+  FV_REQUIRE(nb >= 0 && (int64_t)nb * ntr <= 65535, "batch too large");
+  FV_REQUIRE(upsampfac > 1.0 && eps > 0, "bad eps / upsampfac");
+  if (nb == 0 || modes->m1.empty()) return FV_OK;
+  if (prec == 1) return fv::nufft2d1_fused_impl<float>(plan, prec, bx, by, n_dev, n_cap, scale_host, nb, ntr, W, modes, eps, upsampfac, epi_host);
+  return fv::nufft2d1_fused_impl<double>(plan, prec, bx, by, n_dev, n_cap, scale_host, nb, ntr, W, modes, eps, upsampfac, epi_host);
 }
 
 extern "C" int fv_nufft3(fv_plan* plan, int prec, int dim, const void* x, const void* y, const void* z,

@@ -1,0 +1,468 @@
+// Type-1 transform for gridded arrays, B200 form: the fine grid never exists in global memory.
+//
+//   pass 1  t1_spread_fftx_kernel   one CTA per (strip of R grid rows, frequency, transform):
+//           scan the live sources, warp-ballot-compact those whose w-row footprint touches the
+//           strip, spread them into the shared-memory strip (rows owned by warps: no atomics), FFT every
+//           row along x in shared memory, and write ONLY the columns some baseline needs
+//           (n_cols <= n_modes of the nf columns) to the half-transformed array T[col][row].
+//   pass 2  t1_ffty_gather_kernel   one CTA per (group of needed columns, frequency, transform):
+//           load the columns (contiguous rows), FFT along y in shared memory, then for every
+//           baseline whose first mode number is this column: deconvolve, conjugate if flipped,
+//           and store / accumulate straight into the visibility array (the epilogue).
+//
+// Replaces the spread -> cuFFT -> gather chain of fv_nufft2d1 (finufft.nufft2d1 + mode gather,
+// reference cpu/nufft.py:120-175) for the same kernel, grid size and deconvolution, so the error
+// model is unchanged.  Global traffic per transform drops from ~5 passes over nf^2 cells (memset,
+// atomics, two cuFFT passes) to one write + one read of nf x n_cols cells.
+//
+// The shared-memory FFT is an in-place decimation-in-frequency mixed-radix (4, 2, 5, 3) transform:
+// outputs land in digit-reversed positions, which costs nothing here because both passes read
+// their outputs through a position table.
+#pragma once
+#include <limits.h>
+
+namespace fv {
+
+constexpr int T1_THREADS = 256;
+constexpr int T1_MAX_STAGES = 16;
+
+struct FftStages {
+  int nstage;
+  int radix[T1_MAX_STAGES];
+  unsigned inv_m[T1_MAX_STAGES];   // floor(2^32 / m) + 1 for the stage's sub-length m (exact division for t < 2^16)
+  int tw_off[T1_MAX_STAGES];       // start of the stage's twiddles in the table: entry (q - 1) * m + j holds
+                                   // exp(+2 pi i j q / n): consecutive lanes (j) read consecutive words
+  int tw_len;                      // total table length (<= N)
+};
+
+template <typename C> __device__ __forceinline__ C c_add(C a, C b) { a.x += b.x; a.y += b.y; return a; }
+template <typename C> __device__ __forceinline__ C c_sub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
+template <typename C> __device__ __forceinline__ C c_muli(C a) { C r; r.x = -a.y; r.y = a.x; return r; }   // i * a
+
+// r-point DFTs on registers, sign +1:  y_k = sum_q x_q exp(+2 pi i q k / r)
+template <typename T> __device__ __forceinline__ void dft2(cplx_t<T>* x) {
+  const cplx_t<T> t = c_sub(x[0], x[1]);
+  x[0] = c_add(x[0], x[1]); x[1] = t;
+}
+template <typename T> __device__ __forceinline__ void dft4(cplx_t<T>* x) {
+  const cplx_t<T> t0 = c_add(x[0], x[2]), t1 = c_sub(x[0], x[2]);
+  const cplx_t<T> t2 = c_add(x[1], x[3]), t3 = c_muli(c_sub(x[1], x[3]));
+  x[0] = c_add(t0, t2); x[2] = c_sub(t0, t2); x[1] = c_add(t1, t3); x[3] = c_sub(t1, t3);
+}
+template <typename T> __device__ __forceinline__ void dft3(cplx_t<T>* x) {
+  const T h = T(0.86602540378443864676);
+  const cplx_t<T> s = c_add(x[1], x[2]), d = c_sub(x[1], x[2]);
+  cplx_t<T> m; m.x = x[0].x - T(0.5) * s.x; m.y = x[0].y - T(0.5) * s.y;
+  cplx_t<T> id; id.x = -h * d.y; id.y = h * d.x;
+  x[0] = c_add(x[0], s); x[1] = c_add(m, id); x[2] = c_sub(m, id);
+}
+template <typename T> __device__ __forceinline__ void dft5(cplx_t<T>* x) {
+  const T c1 = T(0.30901699437494742410), c2 = T(-0.80901699437494742410);
+  const T s1 = T(0.95105651629515357212), s2 = T(0.58778525229247312917);
+  const cplx_t<T> a1 = c_add(x[1], x[4]), a2 = c_add(x[2], x[3]);
+  const cplx_t<T> b1 = c_sub(x[1], x[4]), b2 = c_sub(x[2], x[3]);
+  cplx_t<T> r1, r2, i1, i2;
+  r1.x = x[0].x + c1 * a1.x + c2 * a2.x; r1.y = x[0].y + c1 * a1.y + c2 * a2.y;
+  r2.x = x[0].x + c2 * a1.x + c1 * a2.x; r2.y = x[0].y + c2 * a1.y + c1 * a2.y;
+  i1.x = -(s1 * b1.y + s2 * b2.y); i1.y = s1 * b1.x + s2 * b2.x;      // i * (s1 b1 + s2 b2)
+  i2.x = -(s2 * b1.y - s1 * b2.y); i2.y = s2 * b1.x - s1 * b2.x;      // i * (s2 b1 - s1 b2)
+  x[0].x += a1.x + a2.x; x[0].y += a1.y + a2.y;
+  x[1] = c_add(r1, i1); x[4] = c_sub(r1, i1); x[2] = c_add(r2, i2); x[3] = c_sub(r2, i2);
+}
+
+// One DIF stage of radix R over the vectors owned by this warp (loop specialised per radix; indices
+// are plain ints relative to the vector base so the compiler emits immediate-offset LDS/STS).
+template <typename T, int R>
+__device__ __forceinline__ void dft_r(cplx_t<T>* x) {
+  if (R == 2) dft2<T>(x);
+  if (R == 3) dft3<T>(x);
+  if (R == 4) dft4<T>(x);
+  if (R == 5) dft5<T>(x);
+}
+
+// One DIF stage of radix R over the vectors owned by this warp.  Two butterflies per iteration with
+// every load issued before the first store (the butterflies are disjoint, which the compiler cannot
+// prove for shared memory): the second butterfly's loads overlap the first one's arithmetic.
+template <typename T, int R>
+__device__ __forceinline__ void fft_stage(cplx_t<T>* data, int nvec, int pitch, int N, int n, unsigned inv,
+                                          const cplx_t<T>* __restrict__ tws, int lane, int warp, int nwarps) {
+  using C = cplx_t<T>;
+  const int m = n / R, per_vec = N / R;
+  for (int v = warp; v < nvec; v += nwarps) {
+    C* vec = data + v * pitch;
+    for (int t0 = lane; t0 < per_vec; t0 += 64) {
+      const int t1 = t0 + 32;
+      const bool two = t1 < per_vec;
+      const int blk0 = inv ? (int)__umulhi((unsigned)t0, inv) : t0;
+      const int blk1 = inv ? (int)__umulhi((unsigned)t1, inv) : t1;
+      const int j0 = t0 - blk0 * m, j1 = t1 - blk1 * m;
+      const int base0 = blk0 * n + j0, base1 = two ? blk1 * n + j1 : base0;
+      C x[R], y[R], wx[R], wy[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) x[q] = vec[base0 + q * m];
+#pragma unroll
+      for (int q = 0; q < R; ++q) y[q] = vec[base1 + q * m];
+      if (m > 1) {
+#pragma unroll
+        for (int q = 1; q < R; ++q) { wx[q] = tws[(q - 1) * m + j0]; wy[q] = tws[(q - 1) * m + (two ? j1 : j0)]; }
+      }
+      dft_r<T, R>(x);
+      dft_r<T, R>(y);
+      if (m > 1) {
+#pragma unroll
+        for (int q = 1; q < R; ++q) { x[q] = cmul(x[q], wx[q]); y[q] = cmul(y[q], wy[q]); }
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q) vec[base0 + q * m] = x[q];
+      if (two) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) vec[base1 + q * m] = y[q];
+      }
+    }
+  }
+}
+
+// In-place FFT of `nvec` vectors of length N (element stride 1, vector stride `pitch`) held in shared
+// memory; every warp owns whole vectors.  Output X[k] sits at the digit-reversed position pos[k].
+template <typename T>
+__device__ void smem_fft(cplx_t<T>* data, int nvec, int pitch, int N, const cplx_t<T>* __restrict__ tw,
+                         const FftStages& st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  int n = N;
+  for (int s = 0; s < st.nstage; ++s) {
+    const int r = st.radix[s];
+    const unsigned inv = st.inv_m[s];            // 0 when m == 1
+    const cplx_t<T>* tws = tw + st.tw_off[s];
+    switch (r) {
+      case 4: fft_stage<T, 4>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
+      case 2: fft_stage<T, 2>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
+      case 5: fft_stage<T, 5>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
+      default: fft_stage<T, 3>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
+    }
+    __syncwarp();                                // a vector's stages only depend on that vector (one warp)
+    n /= r;
+  }
+}
+
+template <typename T>
+struct T1SpreadArgs {
+  const int32_t* n_dev;
+  int64_t n_cap;
+  int nf, R, pitch, w;
+  T beta, c, halfw;
+  int ntr;
+  const cplx_t<T>* W;            // (nb, ntr, n_cap)
+  // per (frequency, source) fold results from t1_prep_kernel, each (nb, n_cap)
+  const int32_t* ix0; const int32_t* iy0;   // first grid column / row of the footprint (may be < 0)
+  const T* zx; const T* zy;                 // kernel argument of that first cell
+  const cplx_t<T>* tw;           // per-stage twiddle tables (FftStages::tw_off), <= nf entries
+  FftStages st;
+  int ncols;
+  const int32_t* col_pos;        // smem position of each needed column's FFT output (ncols)
+  cplx_t<T>* Tbuf;               // (nb, ntr, ncols, nf)
+  long long* dbg;                // optional per-phase cycle counters (development aid), 8 per CTA
+};
+
+// Fold every (frequency, source) NU point onto the fine grid ONCE per batch (fp64 fold of the
+// working-precision product fl(topo * freq), reference cpu_simulate.py:990-992), so that the strip
+// CTAs of pass 1 only compare integers when they look for their sources.
+template <typename T>
+__global__ void __launch_bounds__(256)
+t1_prep_kernel(const T* __restrict__ bx, const T* __restrict__ by, const int32_t* __restrict__ n_dev,
+               int64_t n_cap, const BatchParams* __restrict__ bp, int nf, int w, int32_t* __restrict__ ix0,
+               int32_t* __restrict__ iy0, T* __restrict__ zx, T* __restrict__ zy) {
+  const int n = *n_dev;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int b = blockIdx.y;
+  const T smul = (T)bp[b].smul;
+  const int64_t o = (int64_t)b * n_cap + s;
+  const double hw = 0.5 * (double)w;
+  const double gx = fold_grid((double)(bx[s] * smul), nf), gix = ceil(gx - hw);
+  const double gy = fold_grid((double)(by[s] * smul), nf), giy = ceil(gy - hw);
+  ix0[o] = (int)gix; zx[o] = (T)(gix - gx);
+  iy0[o] = (int)giy; zy[o] = (T)(giy - gy);
+}
+
+constexpr int T1_RC = 128;        // hit records evaluated and spread per flush chunk
+constexpr int T1_SPT = 4;         // sources scanned per thread per tile (hit list holds one tile's worst case)
+
+// shared-memory bytes of pass 1 besides the strip itself
+template <typename T>
+inline size_t t1_spread_fixed_smem(int nf, int wmax, int threads) {
+  return sizeof(cplx_t<T>) * nf                                    // twiddles
+         + (size_t)T1_SPT * threads * sizeof(int)                   // hit list
+         + (size_t)T1_RC * (sizeof(cplx_t<T>) + 2 * wmax * sizeof(T) + 2 * sizeof(int));
+}
+
+template <typename T, int WT>
+__global__ void __launch_bounds__(768)
+t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
+  using C = cplx_t<T>;
+  extern __shared__ __align__(16) unsigned char t1_smem[];
+  const int w = WT > 0 ? WT : a.w;
+  constexpr int WMAX = WT > 0 ? WT : kMaxW;
+  const int nthr = blockDim.x, lcap = T1_SPT * nthr;
+  C* strip = (C*)t1_smem;                                  // R * pitch
+  C* tw = strip + (size_t)a.R * a.pitch;                   // nf
+  C* rec_w = tw + a.nf;                                    // T1_RC
+  T* rec_kx = (T*)(rec_w + T1_RC);                         // T1_RC * WMAX
+  T* rec_ky = rec_kx + T1_RC * WMAX;                       // T1_RC * WMAX
+  int* rec_i0x = (int*)(rec_ky + T1_RC * WMAX);            // T1_RC
+  int* rec_d = rec_i0x + T1_RC;                            // T1_RC
+  int* lst_s = rec_d + T1_RC;                              // lcap
+  __shared__ int hit_count;
+
+  const int nf = a.nf, pitch = a.pitch;
+  const int bpi = blockIdx.y, b = bpi / a.ntr;
+  const int r0 = blockIdx.x * a.R;
+  const int rows = min(a.R, nf - r0);
+  const int n = *a.n_dev;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  const int rpw = (rows + nwarps - 1) / nwarps;            // strip rows owned by each warp
+  const int rb0 = warp * rpw, rb1 = min(rows, rb0 + rpw);
+  const int G = 32 / w;                                    // footprint rows per warp instruction (multi-row path)
+  // column segments of the thread-per-row path: at least 8 w columns each, one warp per segment
+  const int nseg = min(nwarps, nf / (8 * w));
+  const int seg = nseg > 0 ? (nf + nseg - 1) / nseg : nf;
+  const int jj = lane / w, jx = lane - jj * w;
+  const int32_t* iy0 = a.iy0 + (int64_t)b * a.n_cap;
+  const int32_t* ix0 = a.ix0 + (int64_t)b * a.n_cap;
+  const T* zxp = a.zx + (int64_t)b * a.n_cap;
+  const T* zyp = a.zy + (int64_t)b * a.n_cap;
+  const C* Wp = a.W + (int64_t)bpi * a.n_cap;
+
+  long long tph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tc = clock64();
+#define T1_PHASE(i) do { if (a.dbg) { const long long t_ = clock64(); tph[i] += t_ - tc; tc = t_; } } while (0)
+  for (int i = tid; i < a.R * pitch; i += nthr) strip[i] = make_c<T>(T(0), T(0));
+  for (int i = tid; i < a.st.tw_len; i += nthr) tw[i] = a.tw[i];
+  if (tid == 0) hit_count = 0;
+  __syncthreads();
+  T1_PHASE(0);
+
+  for (int tile = 0; tile < n; tile += T1_SPT * nthr) {
+    // ---- scan: which sources' w-row footprints touch this strip (integer compares only) ---------
+    int yv[T1_SPT];
+#pragma unroll
+    for (int u = 0; u < T1_SPT; ++u) {
+      const int s = tile + u * nthr + tid;
+      yv[u] = s < n ? iy0[s] : INT_MIN;
+    }
+#pragma unroll
+    for (int u = 0; u < T1_SPT; ++u) {
+      bool hit = false;
+      if (yv[u] != INT_MIN) {
+        int d = yv[u] - r0;
+        if (d < 0) d += nf;
+        if (d < 0) d += nf;
+        hit = d < rows || d + w > nf;
+      }
+      const unsigned ball = __ballot_sync(0xffffffffu, hit);
+      int base = 0;
+      if (lane == 0 && ball) base = atomicAdd(&hit_count, __popc(ball));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (hit) lst_s[base + __popc(ball & ((1u << lane) - 1u))] = tile + u * nthr + tid;
+    }
+    __syncthreads();
+    const int nh = hit_count;
+    T1_PHASE(1);
+    tph[7] += nh;
+    // ---- flush: evaluate kernels densely, then spread by row ownership -------------------------
+    for (int c0 = 0; c0 < nh; c0 += T1_RC) {
+      const int cn = min(T1_RC, nh - c0);
+      for (int t = tid; t < 2 * cn; t += nthr) {
+        const int h = t >> 1, dim = t & 1, src = lst_s[c0 + h];
+        T z0;
+        if (dim == 0) {
+          z0 = zxp[src];
+          rec_i0x[h] = ix0[src];
+          rec_w[h] = Wp[src];
+        } else {
+          z0 = zyp[src];
+          int d = iy0[src] - r0;
+          if (d < 0) d += nf;
+          if (d < 0) d += nf;
+          rec_d[h] = d;
+        }
+        T* kk = (dim == 0 ? rec_kx : rec_ky) + h * WMAX;
+#pragma unroll
+        for (int j = 0; j < WMAX; ++j)
+          if (j < w) kk[j] = es_kernel<T>(z0 + (T)j, a.beta, a.c, a.halfw);
+      }
+      __syncthreads();
+      T1_PHASE(2);
+      if (rows <= 32 && nseg > 0) {
+        // Thread-per-row spreading without atomics: lane = strip row, warp = column segment.  A warp
+        // walks the hits whose columns lie wholly inside its segment; every lane whose row is in the
+        // hit's footprint adds the hit's w cells of that row.  Lanes touch different rows, warps
+        // different column ranges, and a thread's own updates are program-ordered: no races, and a
+        // deterministic sum order.  Hits that straddle a segment edge (or wrap) go second, one warp.
+        for (int pass = 0; pass < 2; ++pass) {
+          const long long tp0 = clock64();
+          if (warp < nseg) {
+            for (int hb = 0; hb < cn; hb += 32) {
+              const int hl = hb + lane;
+              int c0w = 0;
+              bool mine = false;
+              if (hl < cn) {
+                c0w = wrap_idx(rec_i0x[hl], nf);
+                const int ks = c0w / seg;
+                const bool interior = c0w + w <= min(nf, (ks + 1) * seg);
+                // pass 0: hits wholly inside my segment; pass 1: hits that start in my segment and
+                // cross its upper edge (different edges are > w columns apart, so warps stay disjoint)
+                mine = ks == warp && interior == (pass == 0);
+              }
+              unsigned mask = __ballot_sync(0xffffffffu, mine);
+              while (mask) {
+                const int sl = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int h = hb + sl;
+                const int c0 = __shfl_sync(0xffffffffu, c0w, sl);
+                int j = lane - rec_d[h];
+                if (j < 0) j += nf;
+                tph[10] += 1;
+                if (lane < rows && j < w) {
+                  const C cw = rec_w[h];
+                  const T ky = rec_ky[h * WMAX + j];
+                  const T cr = cw.x * ky, ci = cw.y * ky;
+                  C* rowp = strip + lane * pitch;
+                  const T* kx = rec_kx + h * WMAX;
+                  // all loads first, then all stores: the w cells are distinct, so the loads pipeline
+                  T kr[WMAX];
+                  C v[WMAX];
+                  int cq[WMAX];
+#pragma unroll
+                  for (int q = 0; q < WMAX; ++q) if (q < w) kr[q] = kx[q];
+#pragma unroll
+                  for (int q = 0; q < WMAX; ++q)
+                    if (q < w) { cq[q] = pass == 0 ? c0 + q : wrap_idx(c0 + q, nf); v[q] = rowp[cq[q]]; }
+#pragma unroll
+                  for (int q = 0; q < WMAX; ++q)
+                    if (q < w) { v[q].x += cr * kr[q]; v[q].y += ci * kr[q]; rowp[cq[q]] = v[q]; }
+                }
+              }
+            }
+          }
+          if (a.dbg) tph[8 + pass] += clock64() - tp0;
+          __syncthreads();
+        }
+      } else if (rb0 < rb1) {
+        // several rows per warp (small grids held whole in one CTA): warp q owns strip rows
+        // [q rpw, (q + 1) rpw); one hit at a time, G of its footprint rows per instruction (lane =
+        // row in group * w + column).  Lanes of one instruction touch distinct cells and no other
+        // warp touches these rows: race-free, deterministic order.
+        const int blk = rb1 - rb0;
+        for (int hb = 0; hb < cn; hb += 32) {
+          const int hl = hb + lane;
+          int ja_l = 0, jb_l = 0, dh_l = 0;
+          if (hl < cn) {
+            dh_l = rec_d[hl];
+            int aoff = dh_l - rb0;
+            if (aoff < 0) aoff += nf;
+            if (aoff < blk) { ja_l = 0; jb_l = min(w, blk - aoff); }
+            else { ja_l = nf - aoff; jb_l = min(w, ja_l + blk); }
+          }
+          unsigned rel = __ballot_sync(0xffffffffu, ja_l < jb_l);
+          while (rel) {
+            const int src_lane = __ffs(rel) - 1;
+            rel &= rel - 1;
+            const int h = hb + src_lane;
+            const int ja = __shfl_sync(0xffffffffu, ja_l, src_lane);
+            const int jb = __shfl_sync(0xffffffffu, jb_l, src_lane);
+            const int dh = __shfl_sync(0xffffffffu, dh_l, src_lane);
+            const C cw = rec_w[h];
+            const T kxv = (jj < G) ? rec_kx[h * WMAX + jx] : T(0);
+            const int col = wrap_idx(rec_i0x[h] + jx, nf);
+            for (int j0 = ja; j0 < jb; j0 += G) {
+              const int j = j0 + jj;
+              if (jj < G && j < jb) {
+                int rr = dh + j;
+                if (rr >= nf) rr -= nf;
+                const T k2 = rec_ky[h * WMAX + j] * kxv;
+                C* cell = strip + rr * pitch + col;
+                C v = *cell;
+                v.x += cw.x * k2; v.y += cw.y * k2;
+                *cell = v;
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+      __syncthreads();
+      T1_PHASE(3);
+    }
+    if (tid == 0) hit_count = 0;
+    __syncthreads();
+  }
+
+  smem_fft<T>(strip, rows, pitch, nf, tw, a.st);
+  T1_PHASE(4);
+  __syncthreads();
+  T1_PHASE(5);
+
+  // needed columns of this strip -> T[col][row] (rows contiguous)
+  C* Tb = a.Tbuf + (int64_t)bpi * a.ncols * nf + r0;
+  const int total = a.ncols * rows;
+  const unsigned inv_rows = rows > 1 ? (unsigned)(((1ull << 32) / (unsigned)rows) + 1ull) : 0u;
+#pragma unroll 4
+  for (int i = tid; i < total; i += nthr) {
+    const int ci = inv_rows ? (int)__umulhi((unsigned)i, inv_rows) : i;
+    const int rr = i - ci * rows;
+    Tb[(int64_t)ci * nf + rr] = strip[rr * pitch + a.col_pos[ci]];
+  }
+  T1_PHASE(6);
+  if (a.dbg && lane == 0 && blockIdx.y == 0 && blockIdx.x < 8)
+    for (int i = 0; i < 12; ++i) atomicAdd((unsigned long long*)&a.dbg[i], (unsigned long long)tph[i]);
+#undef T1_PHASE
+}
+
+template <typename T>
+struct T1GatherArgs {
+  const cplx_t<T>* Tbuf;         // (nb, ntr, ncols, nf)
+  int nf, pitch, ncols, cols_per_cta, ntr;
+  const cplx_t<T>* tw;
+  FftStages st;
+  const int32_t* col_off;        // (ncols + 1) ranges into the column-sorted baseline tables
+  const int32_t* s_k;            // baseline index (position in the caller's m1/m2 arrays)
+  const int32_t* s_pos;          // smem position of the baseline's second mode number
+  const T* s_scale;              // 1 / (phihat(m1) phihat(m2))
+  EpiDev epi;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(T1_THREADS)
+t1_ffty_gather_kernel(T1GatherArgs<T> a) {
+  using C = cplx_t<T>;
+  extern __shared__ __align__(16) unsigned char t1_smem[];
+  C* cols = (C*)t1_smem;                                    // cols_per_cta * pitch
+  C* tw = cols + (size_t)a.cols_per_cta * a.pitch;          // nf
+  const int nf = a.nf, pitch = a.pitch;
+  const int bpi = blockIdx.y, b = bpi / a.ntr, p = bpi - b * a.ntr;
+  const int c0 = blockIdx.x * a.cols_per_cta;
+  const int nc = min(a.cols_per_cta, a.ncols - c0);
+  const int tid = threadIdx.x;
+  const C* Tb = a.Tbuf + ((int64_t)bpi * a.ncols + c0) * nf;
+  for (int i = tid; i < nc * nf; i += blockDim.x) {
+    const int ci = i / nf, rr = i - ci * nf;
+    cols[ci * pitch + rr] = Tb[i];
+  }
+  for (int i = tid; i < a.st.tw_len; i += blockDim.x) tw[i] = a.tw[i];
+  __syncthreads();
+  smem_fft<T>(cols, nc, pitch, nf, tw, a.st);
+  __syncthreads();
+  const int k0 = a.col_off[c0], k1 = a.col_off[c0 + nc];
+  // walk the column-sorted baselines of this CTA's columns
+  for (int kk = k0 + tid; kk < k1; kk += blockDim.x) {
+    // column of kk: binary search in col_off[c0 .. c0 + nc]
+    int lo = 0, hi = nc;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.col_off[c0 + mid] <= kk) lo = mid; else hi = mid; }
+    C v = cols[lo * pitch + a.s_pos[kk]];
+    const T sc = a.s_scale[kk];
+    v.x *= sc; v.y *= sc;
+    epilogue_store(a.epi, b, p, (int64_t)a.s_k[kk], v);
+  }
+}
+
+}  // namespace fv

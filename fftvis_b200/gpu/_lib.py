@@ -59,6 +59,12 @@ _SIGNATURES = {
     "fv_nufft2d1": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                             POINTER(c_double), c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                             c_int64, c_double, c_double, POINTER(fv_epilogue)]),
+    "fv_modeset_create": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_int64, c_int]),
+    "fv_modeset_destroy": (c_int, [c_void_p]),
+    "fv_nufft2d1_fused": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
+                                  POINTER(c_double), c_int, c_int, c_void_p, c_void_p, c_double, c_double,
+                                  POINTER(fv_epilogue)]),
+    "fv_plan_set_option": (c_int, [c_void_p, c_char_p, c_int64]),
     "fv_nufft3": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                           POINTER(c_double), c_void_p, c_void_p, c_void_p, c_int64,
                           POINTER(c_double), POINTER(c_double), c_int, c_int, c_void_p, c_double,

@@ -36,7 +36,7 @@ from ..core import utils as core_utils
 from ..core.simulate import SimulationEngine, default_accuracy_dict
 from . import _lib
 from .beams import DeviceBeam, GPUBeamEvaluator, launch_weights
-from .nufft import NufftPlan
+from .nufft import ModeSet, NufftPlan
 
 logger = logging.getLogger(__name__)
 
@@ -57,6 +57,7 @@ class _PairTable:
     conj: torch.Tensor | None          # uint8 flipped flags (None: none flipped)
     m1: torch.Tensor | None = None     # type 1: signed integer modes (flip already applied)
     m2: torch.Tensor | None = None
+    modes: ModeSet | None = None       # type 1: the same modes bucketed by m1 (fused path)
     uvw: list | None = None            # type 3: per-unit-frequency targets (flip already applied)
     ulim: list | None = None           # type 3: {min, max} of each target coordinate
 
@@ -108,8 +109,12 @@ def _next235even(n: int) -> int:
 class GPUSimulationEngine(SimulationEngine):
     """GPU implementation of the simulation engine."""
 
-    def __init__(self, device=None, freq_batch: int | None = None, grid_budget_bytes: int = 48 << 20):
+    def __init__(self, device=None, freq_batch: int | None = None, grid_budget_bytes: int = 48 << 20,
+                 type1_method: str = "fused"):
+        if type1_method not in ("fused", "cufft"):
+            raise ValueError("type1_method must be 'fused' or 'cufft'")
         self.device = device
+        self.type1_method = type1_method
         self.freq_batch = freq_batch
         self.grid_budget_bytes = int(grid_budget_bytes)
         self.last_fft_ms = None
@@ -239,7 +244,7 @@ class GPUSimulationEngine(SimulationEngine):
                     ant1=torch.as_tensor(i0.astype(np.int32)).to(dev),
                     ant2=torch.as_tensor(i1.astype(np.int32)).to(dev), K=nbeam, nant=nant)
                 pairs.append(self._pair_table(0, 0, np.arange(nbls), np.zeros(nbls, bool), bls,
-                                              is_gridded, is_coplanar, rd, dev, nbls))
+                                              is_gridded, is_coplanar, rd, dev, nbls, n_modes))
             else:
                 upairs, to_bls, to_flip = GPUBeamEvaluator.prepare_beam_evaluation(antnums, baselines, beam_idx)
                 for (bi, bj) in upairs:
@@ -248,12 +253,13 @@ class GPUSimulationEngine(SimulationEngine):
                         continue
                     fl = np.asarray(to_flip[(bi, bj)], dtype=bool)
                     pairs.append(self._pair_table(int(bi), int(bj), idx, fl, bls, is_gridded,
-                                                  is_coplanar, rd, dev, nbls))
+                                                  is_coplanar, rd, dev, nbls, n_modes))
 
         P = 4 if polarized else 1
         fb = self.freq_batch
         if fb is None:
-            fb = self._auto_batch(is_gridded, n_modes, P, precision, eps, float(upsample_factor), n_cap)
+            ncols = max((int(np.unique(pt.m1.cpu().numpy()).size) for pt in pairs), default=None) if is_gridded else None
+            fb = self._auto_batch(is_gridded, n_modes, P, precision, eps, float(upsample_factor), n_cap, ncols)
         return SimulationPlan(
             precision=precision, polarized=polarized, polarized_sky=pol_sky, nfeeds=2 if polarized else 1,
             eps=float(eps), upsample_factor=float(upsample_factor), use_type1=is_gridded,
@@ -263,7 +269,7 @@ class GPUSimulationEngine(SimulationEngine):
             freqs_dev=freqs_d, beams=dbeams, pairs=pairs, basis=basis, freq_batch=int(fb), device=dev)
 
     @staticmethod
-    def _pair_table(bi, bj, idx, fl, bls, is_gridded, is_coplanar, rd, dev, nbls) -> _PairTable:
+    def _pair_table(bi, bj, idx, fl, bls, is_gridded, is_coplanar, rd, dev, nbls, n_modes=None) -> _PairTable:
         all_in_order = idx.size == nbls and np.array_equal(idx, np.arange(nbls))
         kmap = None if all_in_order else torch.as_tensor(idx.astype(np.int32)).to(dev)
         conj = torch.as_tensor(fl.astype(np.uint8)).to(dev) if fl.any() else None
@@ -272,6 +278,7 @@ class GPUSimulationEngine(SimulationEngine):
             m = np.where(fl, -bls[:, idx], bls[:, idx])            # cpu_simulate.py:259
             pt.m1 = torch.as_tensor(np.ascontiguousarray(m[0]).astype(np.int32)).to(dev)
             pt.m2 = torch.as_tensor(np.ascontiguousarray(m[1]).astype(np.int32)).to(dev)
+            pt.modes = ModeSet(m[0], m[1], n_modes)
         else:
             q = np.where(fl, -bls[:, idx], bls[:, idx]).astype(rd)  # cpu_simulate.py:271
             dim = 2 if is_coplanar else 3
@@ -279,20 +286,37 @@ class GPUSimulationEngine(SimulationEngine):
             pt.ulim = [float(v) for d in range(dim) for v in (q[d].min(), q[d].max())]
         return pt
 
-    def _auto_batch(self, type1, n_modes, P, precision, eps, upsampfac, n_cap) -> int:
-        """Frequencies per batch: keep the batch's fine grids near the L2 budget."""
+    def _auto_batch(self, type1, n_modes, P, precision, eps, upsampfac, n_cap, ncols=None) -> int:
+        """Frequencies per batch.  cuFFT type-1 path: keep the batch's fine grids near the L2 budget.
+        Fused type-1 path: keep the half-transformed array T (ncols x nf per frequency and product)
+        inside L2 and make the strip CTAs of pass 1 fill whole waves of the 148 SMs."""
+        import ctypes
         csize = 8 * precision
-        if type1:
-            import ctypes
-            w = ctypes.c_int(0); beta = ctypes.c_double(0)
-            _lib.check(_lib.lib().fv_kernel_params(eps, upsampfac, precision, ctypes.byref(w), ctypes.byref(beta)))
-            nf = _next235even(max(int(upsampfac * n_modes), 2 * w.value))
-            per_f = P * nf * nf * csize
-        else:
-            per_f = self.grid_budget_bytes      # type-3 grids are large: one or a few per batch
-        by_grid = max(1, self.grid_budget_bytes // max(per_f, 1))
         by_w = max(1, (1 << 30) // max(1, P * n_cap * csize))          # strengths buffer <= 1 GiB
-        return int(max(1, min(256, by_grid, by_w)))
+        if not type1:
+            return int(max(1, min(256, by_w, 4)))                      # type-3 grids are large
+        w = ctypes.c_int(0); beta = ctypes.c_double(0)
+        _lib.check(_lib.lib().fv_kernel_params(eps, upsampfac, precision, ctypes.byref(w), ctypes.byref(beta)))
+        nf = _next235even(max(int(upsampfac * n_modes), 2 * w.value))
+        if self.type1_method == "cufft":
+            by_grid = max(1, self.grid_budget_bytes // max(P * nf * nf * csize, 1))
+            return int(max(1, min(256, by_grid, by_w)))
+        per_f = P * (ncols or n_modes) * nf * csize
+        nb_max = int(max(1, min(64, by_w, (96 << 20) // max(per_f, 1))))
+        row_bytes = (nf + 1) * csize
+        if row_bytes * nf <= 160 * 1024:
+            strips = 1
+        else:
+            rows = max(1, min(32, (190 * 1024) // row_bytes))
+            rows -= rows % 8 if rows > 8 else 0
+            strips = -(-nf // rows)
+        best, best_eff = nb_max, 0.0
+        for nb in range(max(1, nb_max // 2), nb_max + 1):
+            ctas = strips * nb * P
+            eff = ctas / (-(-ctas // 148) * 148)
+            if eff >= best_eff - 1e-9:
+                best, best_eff = nb, eff
+        return int(best)
 
     # ------------------------------------------------------------------------------------------
     def _workspace(self, plan: SimulationPlan):
@@ -388,7 +412,10 @@ class GPUSimulationEngine(SimulationEngine):
 
     def _nufft_batch(self, plan, w, nufft, pt, dim, xlim, scale, nb, epi):
         W = w["W"][:nb]
-        if plan.use_type1:
+        if plan.use_type1 and self.type1_method == "fused":
+            nufft.type1_fused(plan.precision, w["xyz"][0], w["xyz"][1], w["n_dev"], scale, W, pt.modes,
+                              plan.eps, plan.upsample_factor, epi)
+        elif plan.use_type1:
             nufft.type1(plan.precision, w["xyz"][0], w["xyz"][1], w["n_dev"], scale, W, plan.n_modes,
                         pt.m1, pt.m2, plan.eps, plan.upsample_factor, epi)
         else:

@@ -8,6 +8,7 @@ the arithmetic is libfftvis_b200's CUDA kernels + cuFFT.  Sign convention exp(+i
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -16,6 +17,34 @@ from . import _lib
 
 _RDT = {1: torch.float32, 2: torch.float64}
 _CDT = {1: torch.complex64, 2: torch.complex128}
+
+
+class ModeSet:
+    """Integer modes (m1, m2) of one beam pair's baselines, bucketed by m1 on the host once
+    (``fv_modeset``): the target set of the fused type-1 transform."""
+
+    def __init__(self, m1, m2, n_modes: int):
+        m1 = np.ascontiguousarray(m1, dtype=np.int32)
+        m2 = np.ascontiguousarray(m2, dtype=np.int32)
+        if m1.shape != m2.shape or m1.ndim != 1:
+            raise ValueError("m1 and m2 must be 1-D arrays of equal length")
+        self.nk = int(m1.size)
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().fv_modeset_create(ctypes.byref(h), m1.ctypes.data, m2.ctypes.data, self.nk,
+                                                int(n_modes)), "fv_modeset_create")
+        self._h = h
+
+    @property
+    def handle(self):
+        return self._h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().fv_modeset_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 class NufftPlan:
@@ -29,6 +58,9 @@ class NufftPlan:
             h = ctypes.c_void_p()
             _lib.check(_lib.lib().fv_plan_create(ctypes.byref(h), self.stream.cuda_stream), "fv_plan_create")
         self._h = h
+        for env, opt in (("FV_T1_ROWS", "t1_rows"), ("FV_T1_COLS", "t1_cols")):   # tuning experiments
+            if os.environ.get(env):
+                self.set_option(opt, int(os.environ[env]))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -70,6 +102,16 @@ class NufftPlan:
             self._h, prec, bx.data_ptr(), by.data_ptr(), n_dev.data_ptr(), n_cap,
             _lib.doubles(scale), nb, ntr, W.data_ptr(), int(n_modes), m1.data_ptr(), m2.data_ptr(),
             m1.numel(), float(eps), float(upsampfac), ctypes.byref(epi)), "fv_nufft2d1")
+
+    def type1_fused(self, prec, bx, by, n_dev, scale, W, modes: ModeSet, eps, upsampfac, epi):
+        nb, ntr, n_cap = W.shape
+        _lib.check(_lib.lib().fv_nufft2d1_fused(
+            self._h, prec, bx.data_ptr(), by.data_ptr(), n_dev.data_ptr(), n_cap, _lib.doubles(scale), nb,
+            ntr, W.data_ptr(), modes.handle, float(eps), float(upsampfac), ctypes.byref(epi)),
+            "fv_nufft2d1_fused")
+
+    def set_option(self, name: str, value: int):
+        _lib.check(_lib.lib().fv_plan_set_option(self._h, name.encode(), int(value)), "fv_plan_set_option")
 
     def type3(self, prec, dim, xyz, n_dev, xlim, uvw, ulim, scale, W, eps, upsampfac, epi):
         nb, ntr, n_cap = W.shape
@@ -137,10 +179,12 @@ def gpu_nufft3d(x, y, z, weights, u, v, w, eps, n_threads: int = 1, upsample_fac
     return _one_shot(3, [x, y, z], weights, [u, v, w], eps, float(upsample_factor))
 
 
-def gpu_nufft2d_type1(x, y, weights, n_modes, index, eps, upsample_factor=2, n_threads: int = 1):
+def gpu_nufft2d_type1(x, y, weights, n_modes, index, eps, upsample_factor=2, n_threads: int = 1,
+                      method: str = "fused"):
     """Type-1 2-D transform onto ``n_modes`` x ``n_modes`` integer modes followed by the gather
     ``model[..., index[0], index[1]]`` (CPU: cpu/nufft.py:120-175).  ``index`` holds signed mode
-    numbers; negative ones address the FFT-ordered negative frequencies, as in the reference."""
+    numbers; negative ones address the FFT-ordered negative frequencies, as in the reference.
+    ``method``: "fused" (shared-memory spread + FFT, the default) or "cufft" (global fine grid)."""
     _lib.require_gpu()
     weights = np.asarray(weights)
     prec = _prec_of(weights)
@@ -162,6 +206,13 @@ def gpu_nufft2d_type1(x, y, weights, n_modes, index, eps, upsample_factor=2, n_t
     out = torch.zeros((1, W.shape[1], m1.numel()), dtype=cdt, device="cuda")
     epi = _lib.make_epilogue(out.data_ptr(), out.stride(0), out.stride(1))
     if n and m1.numel():
-        default_plan().type1(prec, bx, by, n_dev, [1.0], W, n_modes, m1, m2, eps, float(upsample_factor), epi)
+        if method == "fused":
+            modes = ModeSet(m[0], m[1], n_modes)
+            default_plan().type1_fused(prec, bx, by, n_dev, [1.0], W, modes, eps, float(upsample_factor), epi)
+            torch.cuda.current_stream().synchronize()      # modes is released on return
+        elif method == "cufft":
+            default_plan().type1(prec, bx, by, n_dev, [1.0], W, n_modes, m1, m2, eps, float(upsample_factor), epi)
+        else:
+            raise ValueError("method must be 'fused' or 'cufft'")
     res = out[0].cpu().numpy()
     return res[0] if weights.ndim == 1 else res

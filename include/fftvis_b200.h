@@ -162,6 +162,24 @@ int fv_nufft2d1(fv_plan* plan, int prec, const void* bx, const void* by, const i
                 int n_modes, const int32_t* m1, const int32_t* m2, int64_t nk, double eps,
                 double upsampfac, const fv_epilogue* epi_host);
 
+/* type 1, 2-D, fused shared-memory form (same transform, kernel, grid size and deconvolution as
+ * fv_nufft2d1, i.e. finufft.nufft2d1 + the mode gather of cpu/nufft.py:120-175), for arrays whose
+ * baselines are known up front: the fine grid lives only in shared memory (spread + FFT along x per
+ * strip of grid rows; FFT along y + deconvolve + gather per group of needed columns; the inner FFT
+ * is this library's own shared-memory mixed-radix transform, not cuFFT).
+ * An fv_modeset holds the (m1, m2) integer modes of one beam pair's baselines (flip already
+ * applied) bucketed by m1; it is built once on the host. */
+typedef struct fv_modeset fv_modeset;
+int fv_modeset_create(fv_modeset** modes, const int32_t* m1_host, const int32_t* m2_host, int64_t nk,
+                      int n_modes);
+int fv_modeset_destroy(fv_modeset* modes);
+int fv_nufft2d1_fused(fv_plan* plan, int prec, const void* bx, const void* by, const int32_t* n_dev,
+                      int64_t n_cap, const double* scale_host, int nb, int ntr, const void* W,
+                      fv_modeset* modes, double eps, double upsampfac, const fv_epilogue* epi_host);
+/* tuning knobs: "t1_rows" (strip height of the fused type-1 path, 0 = automatic), "t1_cols"
+ * (columns per CTA of its second pass), "max_grid_bytes" */
+int fv_plan_set_option(fv_plan* plan, const char* name, int64_t value);
+
 /* type 3, 2-D / 3-D (cpu_nufft2d / cpu_nufft3d -> finufft.nufft2d3 / nufft3d3, cpu/nufft.py:11-118),
  * batched over nb frequencies:   s_k(b) = fl(base_k * scale[b])   (uvw = bls*freq, :973)
  *   out[b,p,k] = sum_s W[b,p,s] exp(i (u_k x_s + v_k y_s [+ w_k z_s]))

@@ -17,7 +17,8 @@ def _types(prec):
 @pytest.mark.parametrize("prec,eps", [(2, 1e-13), (2, 1e-10), (2, 1e-6), (1, 6e-8), (1, 1e-4)])
 @pytest.mark.parametrize("upsamp", [2.0, 1.25])
 @pytest.mark.parametrize("ntr", [1, 4])
-def test_type1_vs_oracle(prec, eps, upsamp, ntr):
+@pytest.mark.parametrize("method", ["fused", "cufft"])
+def test_type1_vs_oracle(prec, eps, upsamp, ntr, method):
     from fftvis_b200.gpu import gpu_nufft2d_type1
     from oracle import nufft_cpu as nc
     rng = np.random.default_rng(0)
@@ -27,7 +28,7 @@ def test_type1_vs_oracle(prec, eps, upsamp, ntr):
     y = rng.uniform(-40, 40, n).astype(rd)
     c = (rng.normal(size=(ntr, n)) + 1j * rng.normal(size=(ntr, n))).astype(cd)
     idx = rng.integers(-(N // 2), N // 2 + 1, size=(2, 97))
-    got = gpu_nufft2d_type1(x, y, c, N, idx, eps, upsample_factor=upsamp)
+    got = gpu_nufft2d_type1(x, y, c, N, idx, eps, upsample_factor=upsamp, method=method)
     assert got.shape == (ntr, 97) and got.dtype == cd
     want = nc.direct_sum(x, y, None, c, idx[0], idx[1], None)
     cpu = nc.cpu_nufft2d_type1(x, y, c, N, idx, eps, upsamp)
@@ -70,6 +71,40 @@ def test_type3_vs_oracle(prec, eps, dim, upsamp):
         tol = max(3e-5, 3 * relerr(cpu, want))
     assert got.shape == want.shape
     assert relerr(got, want) < tol
+
+
+@pytest.mark.parametrize("n_modes,rows", [(465, 0), (465, 7), (121, 0), (41, 0), (41, 16), (7, 0), (251, 5)])
+@pytest.mark.parametrize("prec", [1, 2])
+def test_type1_fused_grid_sizes_and_strip_heights(n_modes, rows, prec):
+    """Fused path on the grid sizes of the BASELINE configs (nf = 960, 250, 90, 30, 512) with
+    automatic and forced strip heights (strips that do not divide nf, single-strip grids), against
+    the direct sum and the cuFFT path."""
+    from fftvis_b200.gpu import gpu_nufft2d_type1
+    from fftvis_b200.gpu.nufft import default_plan
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(n_modes + rows)
+    n, nk = 3000, 400
+    rd, cd = _types(prec)
+    eps = 6e-8 if prec == 1 else 1e-12
+    x = rng.uniform(-60, 60, n).astype(rd)
+    y = rng.uniform(-60, 60, n).astype(rd)
+    c = (rng.normal(size=(2, n)) + 1j * rng.normal(size=(2, n))).astype(cd)
+    h = n_modes // 2
+    idx = rng.integers(-h, h + 1, size=(2, nk))
+    idx[:, :4] = [[-h, h, 0, h], [h, -h, 0, h]]
+    plan = default_plan()
+    plan.set_option("t1_rows", rows)
+    try:
+        got = gpu_nufft2d_type1(x, y, c, n_modes, idx, eps, method="fused")
+    finally:
+        plan.set_option("t1_rows", 0)
+    ref = gpu_nufft2d_type1(x, y, c, n_modes, idx, eps, method="cufft")
+    want = nc.direct_sum(x, y, None, c, idx[0], idx[1], None)
+    if prec == 2:
+        assert relerr(got, want) < 10 * eps
+        assert relerr(got, ref) < 10 * eps
+    else:
+        assert relerr(got, want) < max(3 * relerr(ref, want), 3e-5)
 
 
 def test_type3_offcentre_points_and_targets():
@@ -133,9 +168,17 @@ def test_frequency_batched_type1_and_type3_match_one_by_one():
     plan.type1(2, t(bx, torch.float64), t(by, torch.float64), n_dev, scale, t(W, torch.complex128), 21,
                t(m[0], torch.int32), t(m[1], torch.int32), 1e-12, 2.0, epi)
     got = out.cpu().numpy()
+    from fftvis_b200.gpu.nufft import ModeSet
+    out2 = torch.zeros_like(out)
+    epi2 = _lib.make_epilogue(out2.data_ptr(), out2.stride(0), out2.stride(1))
+    modes = ModeSet(m[0], m[1], 21)
+    plan.type1_fused(2, t(bx, torch.float64), t(by, torch.float64), n_dev, scale, t(W, torch.complex128), modes,
+                     1e-12, 2.0, epi2)
+    got2 = out2.cpu().numpy()
     for b in range(nb):
         want = nc.direct_sum(bx * scale[b], by * scale[b], None, W[b], m[0], m[1], None)
         assert relerr(got[b], want) < 1e-11
+        assert relerr(got2[b], want) < 1e-11
     # type 3: targets scale with the frequency
     x = [2 * np.pi * rng.uniform(-0.6, 0.6, n) for _ in range(2)]
     u = [rng.uniform(-0.08, 0.08, nk) for _ in range(2)]

@@ -158,6 +158,20 @@ def test_evaluate_vis_chunk_slices_match_simulate():
     np.testing.assert_allclose(blk[0, :, 0, 0, :].T, full[2:5, 1], rtol=1e-12, atol=1e-12)
 
 
+def test_type1_fused_and_cufft_paths_agree():
+    from fftvis_b200 import AiryBeam, HERA_LOCATION, synth
+    from fftvis_b200.gpu import GPUSimulationEngine
+    ants = hex_ants(4)
+    freqs = np.linspace(100e6, 200e6, 9)
+    ra, dec, flux = small_sky(2000, freqs)
+    beam = synth.synthetic_uvbeam(freqs, naz=72, nza=37)
+    args = (ants, freqs, flux, [beam], ra, dec, TIMES, HERA_LOCATION)
+    kw = dict(precision=2, eps=1e-12, polarized=True, beam_spline_opts={"order": 1})
+    a = GPUSimulationEngine(type1_method="fused", freq_batch=4).simulate(*args, **kw)
+    b = GPUSimulationEngine(type1_method="cufft", freq_batch=4).simulate(*args, **kw)
+    assert relerr(a, b) < 1e-11
+
+
 def test_f32_close_to_f64_and_no_sources_above_horizon():
     """reference tests/test_wrapper.py:318 (rtol = atol = 1e-5 there, on O(1) visibilities)."""
     from fftvis_b200 import AiryBeam, HERA_LOCATION, simulate_vis
