@@ -1,0 +1,62 @@
+"""Host-side multi-rank logic on CPU: frequency sharding and the slab gather over ``gloo`` with
+world_size 2 (the NCCL path runs the same code on the GPU box)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fftvis_b200.gpu.distributed import gather_slabs, shard_frequencies
+
+
+def test_shard_frequencies_balanced_and_contiguous():
+    assert shard_frequencies(1024, 8) == [(i * 128, (i + 1) * 128) for i in range(8)]
+    s = shard_frequencies(10, 4)
+    assert s == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard_frequencies(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    for nf, w in [(1, 1), (7, 3), (1024, 5)]:
+        s = shard_frequencies(nf, w)
+        assert s[0][0] == 0 and s[-1][1] == nf and all(a[1] == b[0] for a, b in zip(s, s[1:]))
+        sizes = [hi - lo for lo, hi in s]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, nf, dst, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shards = shard_frequencies(nf, world)
+        lo, hi = shards[rank]
+        rng = np.random.default_rng(0)
+        full = rng.normal(size=(nf, 3, 4, 5)) + 1j * rng.normal(size=(nf, 3, 4, 5))
+        local = torch.as_tensor(full[lo:hi].copy())
+        got = gather_slabs(local, shards, dst=dst)
+        if dst is None or rank == dst:
+            q.put((rank, bool(np.array_equal(got.numpy(), full))))
+        else:
+            q.put((rank, got is None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nf,dst", [(7, 0), (8, None), (1, 0)])
+def test_gather_slabs_gloo_world2(nf, dst):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nf, dst, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
