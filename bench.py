@@ -151,7 +151,9 @@ def cpu_sample(w, nbls, budget_s: float = 15.0):
     """Time oracle.pipeline.simulate_cpu on a bounded (time, frequency) sample of the workload with
     every host core; returns (terms/s, description, cores, seconds)."""
     from oracle import nufft_cpu, pipeline
-    cores = nufft_cpu.max_threads()
+    # every host core, whatever OMP_NUM_THREADS says (torchrun sets it to 1): the oracle's OpenMP
+    # regions take an explicit thread count
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     beam = w["beam"] if w["polarized"] else w["beam"].to_power()
     base = dict(precision=w["precision"], polarized=w["polarized"], nthreads=cores, **w["kwargs"])
 
@@ -235,6 +237,7 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device (fftvis_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import fftvis_b200

@@ -683,10 +683,11 @@ static int get_smem_fft(fv_plan* P, int prec, int64_t nf, fv_plan::SmemFft** out
   auto it = P->smem_ffts.find(key);
   if (it != P->smem_ffts.end()) { *out = &it->second; return FV_OK; }
   fv_plan::SmemFft f;
-  // factor order: 4s, then a 2, then 5s, then 3s (odd radices last keep the late, short-stride
+  // factor order: 8s, a 4, a 2, then 5s, then 3s (odd radices last keep the late, short-stride
   // stages free of shared-memory bank conflicts)
   int64_t n = nf;
   std::vector<int> rad;
+  while (n % 8 == 0) { rad.push_back(8); n /= 8; }
   while (n % 4 == 0) { rad.push_back(4); n /= 4; }
   while (n % 2 == 0) { rad.push_back(2); n /= 2; }
   while (n % 5 == 0) { rad.push_back(5); n /= 5; }
@@ -835,7 +836,7 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   // (one row per warp) if that fits, else 8 rows x 256 threads
   // strip height R: the whole grid when it fits one CTA, else as many rows as shared memory holds
   // (<= 32); one warp per strip row (256..768 threads): the row FFTs are warp tasks
-  auto thr_for = [](int64_t rows) { return (int)std::min<int64_t>(768, std::max<int64_t>(256, 32 * rows)); };
+  auto thr_for = [](int64_t rows) { return (int)std::min<int64_t>(t1_limits<T>::spread_threads, std::max<int64_t>(256, 32 * rows)); };
   int R;
   if (P->t1_rows > 0) R = (int)std::min<int64_t>(P->t1_rows, nf);
   else if (t1_spread_fixed_smem<T>((int)nf, wmax, thr_for(nf)) + row_bytes * nf <= 200 * 1024) R = (int)nf;
@@ -888,8 +889,8 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
       cudaMemcpyAsync(hcyc, dbg_dev, 96, cudaMemcpyDeviceToHost, P->stream);
       cudaStreamSynchronize(P->stream);
       const double nw = 8.0 * (threads / 32);
-      fprintf(stderr, "[fv] t1 pass-1 cycles/warp: zero %.0f scan %.0f fill %.0f spread %.0f fft %.0f fftwait %.0f write %.0f hits/strip %.0f passA %.0f passB %.0f hits/warp %.1f\n",
-              hcyc[0] / nw, hcyc[1] / nw, hcyc[2] / nw, hcyc[3] / nw, hcyc[4] / nw, hcyc[5] / nw, hcyc[6] / nw, hcyc[7] / nw, hcyc[8] / nw, hcyc[9] / nw, hcyc[10] / nw);
+      fprintf(stderr, "[fv] t1 pass-1 cycles/warp: zero %.0f scan %.0f fill %.0f spread %.0f fft %.0f fftwait %.0f write %.0f hits/strip %.0f passA %.0f passB %.0f hits/warp %.1f hitcycles %.0f\n",
+              hcyc[0] / nw, hcyc[1] / nw, hcyc[2] / nw, hcyc[3] / nw, hcyc[4] / nw, hcyc[5] / nw, hcyc[6] / nw, hcyc[7] / nw, hcyc[8] / nw, hcyc[9] / nw, hcyc[10] / nw, hcyc[11] / nw);
     }
   }
   // ---- pass 2: FFT along y + deconvolve + gather -----------------------------------------------

@@ -72,8 +72,33 @@ template <typename T> __device__ __forceinline__ void dft5(cplx_t<T>* x) {
 
 // One DIF stage of radix R over the vectors owned by this warp (loop specialised per radix; indices
 // are plain ints relative to the vector base so the compiler emits immediate-offset LDS/STS).
+template <typename T> __device__ __forceinline__ void dft8(cplx_t<T>* x) {
+  using C = cplx_t<T>;
+  const T h = T(0.70710678118654752440);
+  // three radix-2 levels, decimation in frequency, then the bit-reversed outputs are put in order
+  C a[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { a[q] = c_add(x[q], x[q + 4]); a[q + 4] = c_sub(x[q], x[q + 4]); }
+  // twiddles w8^q on the lower half, w8 = exp(+i pi / 4)
+  { C t = a[5]; a[5].x = h * (t.x - t.y); a[5].y = h * (t.x + t.y); }
+  a[6] = c_muli(a[6]);
+  { C t = a[7]; a[7].x = -h * (t.x + t.y); a[7].y = h * (t.x - t.y); }
+  C b[8];
+#pragma unroll
+  for (int g = 0; g < 8; g += 4) {
+    b[g] = c_add(a[g], a[g + 2]); b[g + 2] = c_sub(a[g], a[g + 2]);
+    b[g + 1] = c_add(a[g + 1], a[g + 3]); b[g + 3] = c_muli(c_sub(a[g + 1], a[g + 3]));
+  }
+  // last level: pairs (0,1), (2,3), (4,5), (6,7) -> outputs k = 0,4 | 2,6 | 1,5 | 3,7
+  x[0] = c_add(b[0], b[1]); x[4] = c_sub(b[0], b[1]);
+  x[2] = c_add(b[2], b[3]); x[6] = c_sub(b[2], b[3]);
+  x[1] = c_add(b[4], b[5]); x[5] = c_sub(b[4], b[5]);
+  x[3] = c_add(b[6], b[7]); x[7] = c_sub(b[6], b[7]);
+}
+
 template <typename T, int R>
 __device__ __forceinline__ void dft_r(cplx_t<T>* x) {
+  if (R == 8) dft8<T>(x);
   if (R == 2) dft2<T>(x);
   if (R == 3) dft3<T>(x);
   if (R == 4) dft4<T>(x);
@@ -90,6 +115,29 @@ __device__ __forceinline__ void fft_stage(cplx_t<T>* data, int nvec, int pitch, 
   const int m = n / R, per_vec = N / R;
   for (int v = warp; v < nvec; v += nwarps) {
     C* vec = data + v * pitch;
+    if (R >= 8) {
+      // wide butterfly: one per iteration (register budget), loads before stores
+      for (int t = lane; t < per_vec; t += 32) {
+        const int blk = inv ? (int)__umulhi((unsigned)t, inv) : t;
+        const int j = t - blk * m;
+        const int base = blk * n + j;
+        C x[R], wx[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = vec[base + q * m];
+        if (m > 1) {
+#pragma unroll
+          for (int q = 1; q < R; ++q) wx[q] = tws[(q - 1) * m + j];
+        }
+        dft_r<T, R>(x);
+        if (m > 1) {
+#pragma unroll
+          for (int q = 1; q < R; ++q) x[q] = cmul(x[q], wx[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) vec[base + q * m] = x[q];
+      }
+      continue;
+    }
     for (int t0 = lane; t0 < per_vec; t0 += 64) {
       const int t1 = t0 + 32;
       const bool two = t1 < per_vec;
@@ -134,6 +182,7 @@ __device__ void smem_fft(cplx_t<T>* data, int nvec, int pitch, int N, const cplx
     const unsigned inv = st.inv_m[s];            // 0 when m == 1
     const cplx_t<T>* tws = tw + st.tw_off[s];
     switch (r) {
+      case 8: fft_stage<T, 8>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
       case 4: fft_stage<T, 4>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
       case 2: fft_stage<T, 2>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
       case 5: fft_stage<T, 5>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
@@ -192,11 +241,16 @@ template <typename T>
 inline size_t t1_spread_fixed_smem(int nf, int wmax, int threads) {
   return sizeof(cplx_t<T>) * nf                                    // twiddles
          + (size_t)T1_SPT * threads * sizeof(int)                   // hit list
-         + (size_t)T1_RC * (sizeof(cplx_t<T>) + 2 * wmax * sizeof(T) + 2 * sizeof(int));
+         + sizeof(int) * nf                                         // needed-column positions
+         + (size_t)T1_RC * (sizeof(cplx_t<T>) + 2 * wmax * sizeof(T) + 3 * sizeof(int));
 }
 
+template <typename T> struct t1_limits;
+template <> struct t1_limits<float> { static constexpr int spread_threads = 768, gather_blocks = 3; };
+template <> struct t1_limits<double> { static constexpr int spread_threads = 384, gather_blocks = 1; };
+
 template <typename T, int WT>
-__global__ void __launch_bounds__(768)
+__global__ void __launch_bounds__(t1_limits<T>::spread_threads)
 t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   using C = cplx_t<T>;
   extern __shared__ __align__(16) unsigned char t1_smem[];
@@ -210,7 +264,9 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   T* rec_ky = rec_kx + T1_RC * WMAX;                       // T1_RC * WMAX
   int* rec_i0x = (int*)(rec_ky + T1_RC * WMAX);            // T1_RC
   int* rec_d = rec_i0x + T1_RC;                            // T1_RC
-  int* lst_s = rec_d + T1_RC;                              // lcap
+  int* rec_key = rec_d + T1_RC;                            // T1_RC: 2 * column segment + (straddles its edge)
+  int* lst_s = rec_key + T1_RC;                            // lcap
+  int* colp = lst_s + lcap;                                // ncols (<= nf)
   __shared__ int hit_count;
 
   const int nf = a.nf, pitch = a.pitch;
@@ -222,8 +278,8 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   const int rpw = (rows + nwarps - 1) / nwarps;            // strip rows owned by each warp
   const int rb0 = warp * rpw, rb1 = min(rows, rb0 + rpw);
   const int G = 32 / w;                                    // footprint rows per warp instruction (multi-row path)
-  // column segments of the thread-per-row path: at least 8 w columns each, one warp per segment
-  const int nseg = min(nwarps, nf / (8 * w));
+  // column segments of the thread-per-row path: at least 4 w columns each, one warp per segment
+  const int nseg = min(nwarps, nf / (4 * w));
   const int seg = nseg > 0 ? (nf + nseg - 1) / nseg : nf;
   const int jj = lane / w, jx = lane - jj * w;
   const int32_t* iy0 = a.iy0 + (int64_t)b * a.n_cap;
@@ -237,6 +293,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
 #define T1_PHASE(i) do { if (a.dbg) { const long long t_ = clock64(); tph[i] += t_ - tc; tc = t_; } } while (0)
   for (int i = tid; i < a.R * pitch; i += nthr) strip[i] = make_c<T>(T(0), T(0));
   for (int i = tid; i < a.st.tw_len; i += nthr) tw[i] = a.tw[i];
+  for (int i = tid; i < a.ncols; i += nthr) colp[i] = a.col_pos[i];
   if (tid == 0) hit_count = 0;
   __syncthreads();
   T1_PHASE(0);
@@ -249,6 +306,8 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
       const int s = tile + u * nthr + tid;
       yv[u] = s < n ? iy0[s] : INT_MIN;
     }
+    unsigned ball[T1_SPT];
+    int cnt = 0;
 #pragma unroll
     for (int u = 0; u < T1_SPT; ++u) {
       bool hit = false;
@@ -258,11 +317,16 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
         if (d < 0) d += nf;
         hit = d < rows || d + w > nf;
       }
-      const unsigned ball = __ballot_sync(0xffffffffu, hit);
-      int base = 0;
-      if (lane == 0 && ball) base = atomicAdd(&hit_count, __popc(ball));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (hit) lst_s[base + __popc(ball & ((1u << lane) - 1u))] = tile + u * nthr + tid;
+      ball[u] = __ballot_sync(0xffffffffu, hit);
+      cnt += __popc(ball[u]);
+    }
+    int base = 0;
+    if (lane == 0 && cnt) base = atomicAdd(&hit_count, cnt);     // one reservation per warp and tile
+    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+    for (int u = 0; u < T1_SPT; ++u) {
+      if ((ball[u] >> lane) & 1u) lst_s[base + __popc(ball[u] & ((1u << lane) - 1u))] = tile + u * nthr + tid;
+      base += __popc(ball[u]);
     }
     __syncthreads();
     const int nh = hit_count;
@@ -276,7 +340,10 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
         T z0;
         if (dim == 0) {
           z0 = zxp[src];
-          rec_i0x[h] = ix0[src];
+          const int c0w = wrap_idx(ix0[src], nf);
+          rec_i0x[h] = c0w;
+          const int ks = c0w / seg;
+          rec_key[h] = 2 * ks + (c0w + w <= min(nf, (ks + 1) * seg) ? 0 : 1);
           rec_w[h] = Wp[src];
         } else {
           z0 = zyp[src];
@@ -303,16 +370,10 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
           if (warp < nseg) {
             for (int hb = 0; hb < cn; hb += 32) {
               const int hl = hb + lane;
-              int c0w = 0;
-              bool mine = false;
-              if (hl < cn) {
-                c0w = wrap_idx(rec_i0x[hl], nf);
-                const int ks = c0w / seg;
-                const bool interior = c0w + w <= min(nf, (ks + 1) * seg);
-                // pass 0: hits wholly inside my segment; pass 1: hits that start in my segment and
-                // cross its upper edge (different edges are > w columns apart, so warps stay disjoint)
-                mine = ks == warp && interior == (pass == 0);
-              }
+              // pass 0: hits wholly inside my segment; pass 1: hits that start in my segment and
+              // cross its upper edge (different edges are > w columns apart, so warps stay disjoint)
+              const bool mine = hl < cn && rec_key[hl] == 2 * warp + pass;
+              const int c0w = mine ? rec_i0x[hl] : 0;
               unsigned mask = __ballot_sync(0xffffffffu, mine);
               while (mask) {
                 const int sl = __ffs(mask) - 1;
@@ -322,6 +383,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
                 int j = lane - rec_d[h];
                 if (j < 0) j += nf;
                 tph[10] += 1;
+                const long long th0 = a.dbg ? clock64() : 0;
                 if (lane < rows && j < w) {
                   const C cw = rec_w[h];
                   const T ky = rec_ky[h * WMAX + j];
@@ -341,6 +403,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
                   for (int q = 0; q < WMAX; ++q)
                     if (q < w) { v[q].x += cr * kr[q]; v[q].y += ci * kr[q]; rowp[cq[q]] = v[q]; }
                 }
+                if (a.dbg) { __syncwarp(); tph[11] += clock64() - th0; }
               }
             }
           }
@@ -410,7 +473,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   for (int i = tid; i < total; i += nthr) {
     const int ci = inv_rows ? (int)__umulhi((unsigned)i, inv_rows) : i;
     const int rr = i - ci * rows;
-    Tb[(int64_t)ci * nf + rr] = strip[rr * pitch + a.col_pos[ci]];
+    Tb[(int64_t)ci * nf + rr] = strip[rr * pitch + colp[ci]];
   }
   T1_PHASE(6);
   if (a.dbg && lane == 0 && blockIdx.y == 0 && blockIdx.x < 8)
@@ -432,7 +495,7 @@ struct T1GatherArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(T1_THREADS)
+__global__ void __launch_bounds__(T1_THREADS, t1_limits<T>::gather_blocks)
 t1_ffty_gather_kernel(T1GatherArgs<T> a) {
   using C = cplx_t<T>;
   extern __shared__ __align__(16) unsigned char t1_smem[];
