@@ -683,13 +683,14 @@ static int get_smem_fft(fv_plan* P, int prec, int64_t nf, fv_plan::SmemFft** out
   auto it = P->smem_ffts.find(key);
   if (it != P->smem_ffts.end()) { *out = &it->second; return FV_OK; }
   fv_plan::SmemFft f;
-  // factor order: 8s, a 4, a 2, then 5s, then 3s (odd radices last keep the late, short-stride
+  // factor order: 8s, a 4, a 2, then 15s, 5s, 3s (odd radices last keep the late, short-stride
   // stages free of shared-memory bank conflicts)
   int64_t n = nf;
   std::vector<int> rad;
   while (n % 8 == 0) { rad.push_back(8); n /= 8; }
   while (n % 4 == 0) { rad.push_back(4); n /= 4; }
   while (n % 2 == 0) { rad.push_back(2); n /= 2; }
+  while (n % 15 == 0) { rad.push_back(15); n /= 15; }
   while (n % 5 == 0) { rad.push_back(5); n /= 5; }
   while (n % 3 == 0) { rad.push_back(3); n /= 3; }
   if (n != 1 || (int)rad.size() > T1_MAX_STAGES || nf >= 65536) {

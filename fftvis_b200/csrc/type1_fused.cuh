@@ -96,8 +96,28 @@ template <typename T> __device__ __forceinline__ void dft8(cplx_t<T>* x) {
   x[3] = c_add(b[6], b[7]); x[7] = c_sub(b[6], b[7]);
 }
 
+// 15-point DFT by the Good-Thomas prime-factor map (3 x 5, no twiddles): input n = (5 n1 + 3 n2)
+// mod 15, output k = (10 k1 + 6 k2) mod 15; all index shuffling is register renaming.
+template <typename T> __device__ __forceinline__ void dft15(cplx_t<T>* x) {
+  using C = cplx_t<T>;
+  C a[3][5];
+#pragma unroll
+  for (int n2 = 0; n2 < 5; ++n2) {
+    C c[3] = {x[(3 * n2) % 15], x[(5 + 3 * n2) % 15], x[(10 + 3 * n2) % 15]};
+    dft3<T>(c);
+    a[0][n2] = c[0]; a[1][n2] = c[1]; a[2][n2] = c[2];
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 3; ++k1) {
+    dft5<T>(a[k1]);
+#pragma unroll
+    for (int k2 = 0; k2 < 5; ++k2) x[(10 * k1 + 6 * k2) % 15] = a[k1][k2];
+  }
+}
+
 template <typename T, int R>
 __device__ __forceinline__ void dft_r(cplx_t<T>* x) {
+  if (R == 15) dft15<T>(x);
   if (R == 8) dft8<T>(x);
   if (R == 2) dft2<T>(x);
   if (R == 3) dft3<T>(x);
@@ -121,20 +141,18 @@ __device__ __forceinline__ void fft_stage(cplx_t<T>* data, int nvec, int pitch, 
         const int blk = inv ? (int)__umulhi((unsigned)t, inv) : t;
         const int j = t - blk * m;
         const int base = blk * n + j;
-        C x[R], wx[R];
+        C x[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) x[q] = vec[base + q * m];
-        if (m > 1) {
-#pragma unroll
-          for (int q = 1; q < R; ++q) wx[q] = tws[(q - 1) * m + j];
-        }
         dft_r<T, R>(x);
+        vec[base] = x[0];
         if (m > 1) {
 #pragma unroll
-          for (int q = 1; q < R; ++q) x[q] = cmul(x[q], wx[q]);
-        }
+          for (int q = 1; q < R; ++q) vec[base + q * m] = cmul(x[q], tws[(q - 1) * m + j]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < R; ++q) vec[base + q * m] = x[q];
+          for (int q = 1; q < R; ++q) vec[base + q] = x[q];
+        }
       }
       continue;
     }
@@ -182,6 +200,7 @@ __device__ void smem_fft(cplx_t<T>* data, int nvec, int pitch, int N, const cplx
     const unsigned inv = st.inv_m[s];            // 0 when m == 1
     const cplx_t<T>* tws = tw + st.tw_off[s];
     switch (r) {
+      case 15: fft_stage<T, 15>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
       case 8: fft_stage<T, 8>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
       case 4: fft_stage<T, 4>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
       case 2: fft_stage<T, 2>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
@@ -234,6 +253,7 @@ t1_prep_kernel(const T* __restrict__ bx, const T* __restrict__ by, const int32_t
 }
 
 constexpr int T1_RC = 128;        // hit records evaluated and spread per flush chunk
+constexpr int T1_MAXSEG = 24;     // column segments (= warps) of the thread-per-row spreader
 constexpr int T1_SPT = 4;         // sources scanned per thread per tile (hit list holds one tile's worst case)
 
 // shared-memory bytes of pass 1 besides the strip itself
@@ -242,11 +262,12 @@ inline size_t t1_spread_fixed_smem(int nf, int wmax, int threads) {
   return sizeof(cplx_t<T>) * nf                                    // twiddles
          + (size_t)T1_SPT * threads * sizeof(int)                   // hit list
          + sizeof(int) * nf                                         // needed-column positions
-         + (size_t)T1_RC * (sizeof(cplx_t<T>) + 2 * wmax * sizeof(T) + 3 * sizeof(int));
+         + (size_t)2 * T1_MAXSEG * (sizeof(int) + T1_RC)            // per-segment hit counters + lists
+         + (size_t)T1_RC * (sizeof(cplx_t<T>) + 2 * wmax * sizeof(T) + 2 * sizeof(int));
 }
 
 template <typename T> struct t1_limits;
-template <> struct t1_limits<float> { static constexpr int spread_threads = 768, gather_blocks = 3; };
+template <> struct t1_limits<float> { static constexpr int spread_threads = 768, gather_blocks = 2; };
 template <> struct t1_limits<double> { static constexpr int spread_threads = 384, gather_blocks = 1; };
 
 template <typename T, int WT>
@@ -264,9 +285,10 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   T* rec_ky = rec_kx + T1_RC * WMAX;                       // T1_RC * WMAX
   int* rec_i0x = (int*)(rec_ky + T1_RC * WMAX);            // T1_RC
   int* rec_d = rec_i0x + T1_RC;                            // T1_RC
-  int* rec_key = rec_d + T1_RC;                            // T1_RC: 2 * column segment + (straddles its edge)
-  int* lst_s = rec_key + T1_RC;                            // lcap
+  int* lst_s = rec_d + T1_RC;                              // lcap
   int* colp = lst_s + lcap;                                // ncols (<= nf)
+  int* seg_cnt = colp + a.nf;                              // 2 * T1_MAXSEG: [2 * segment + straddles-its-edge]
+  unsigned char* seg_list = (unsigned char*)(seg_cnt + 2 * T1_MAXSEG);   // 2 * T1_MAXSEG * T1_RC
   __shared__ int hit_count;
 
   const int nf = a.nf, pitch = a.pitch;
@@ -279,7 +301,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   const int rb0 = warp * rpw, rb1 = min(rows, rb0 + rpw);
   const int G = 32 / w;                                    // footprint rows per warp instruction (multi-row path)
   // column segments of the thread-per-row path: at least 4 w columns each, one warp per segment
-  const int nseg = min(nwarps, nf / (4 * w));
+  const int nseg = min(min(nwarps, T1_MAXSEG), nf / (4 * w));
   const int seg = nseg > 0 ? (nf + nseg - 1) / nseg : nf;
   const int jj = lane / w, jx = lane - jj * w;
   const int32_t* iy0 = a.iy0 + (int64_t)b * a.n_cap;
@@ -295,6 +317,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   for (int i = tid; i < a.st.tw_len; i += nthr) tw[i] = a.tw[i];
   for (int i = tid; i < a.ncols; i += nthr) colp[i] = a.col_pos[i];
   if (tid == 0) hit_count = 0;
+  if (tid < 2 * T1_MAXSEG) seg_cnt[tid] = 0;
   __syncthreads();
   T1_PHASE(0);
 
@@ -342,8 +365,11 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
           z0 = zxp[src];
           const int c0w = wrap_idx(ix0[src], nf);
           rec_i0x[h] = c0w;
-          const int ks = c0w / seg;
-          rec_key[h] = 2 * ks + (c0w + w <= min(nf, (ks + 1) * seg) ? 0 : 1);
+          if (nseg > 0) {
+            const int ks = c0w / seg;
+            const int key = 2 * ks + (c0w + w <= min(nf, (ks + 1) * seg) ? 0 : 1);
+            seg_list[key * T1_RC + atomicAdd(&seg_cnt[key], 1)] = (unsigned char)h;
+          }
           rec_w[h] = Wp[src];
         } else {
           z0 = zyp[src];
@@ -368,22 +394,24 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
         for (int pass = 0; pass < 2; ++pass) {
           const long long tp0 = clock64();
           if (warp < nseg) {
-            for (int hb = 0; hb < cn; hb += 32) {
-              const int hl = hb + lane;
-              // pass 0: hits wholly inside my segment; pass 1: hits that start in my segment and
-              // cross its upper edge (different edges are > w columns apart, so warps stay disjoint)
-              const bool mine = hl < cn && rec_key[hl] == 2 * warp + pass;
-              const int c0w = mine ? rec_i0x[hl] : 0;
-              unsigned mask = __ballot_sync(0xffffffffu, mine);
-              while (mask) {
-                const int sl = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int h = hb + sl;
-                const int c0 = __shfl_sync(0xffffffffu, c0w, sl);
+            // pass 0: hits wholly inside my segment; pass 1: hits that start in my segment and cross
+            // its upper edge (different edges are > w columns apart, so warps stay disjoint).  The
+            // list was filled with atomics; 32 entries at a time are taken in ascending hit order so
+            // that the sum order does not depend on the race.
+            const int key = 2 * warp + pass;
+            const int L = seg_cnt[key];
+            for (int lb = 0; lb < L; lb += 32) {
+              const int ln = min(32, L - lb);
+              const int e = lane < ln ? (int)seg_list[key * T1_RC + lb + lane] : INT_MAX;
+              int rank = 0;
+              for (int k = 0; k < ln; ++k) rank += __shfl_sync(0xffffffffu, e, k) < e ? 1 : 0;
+              for (int r = 0; r < ln; ++r) {
+                const int sl = __ffs(__ballot_sync(0xffffffffu, lane < ln && rank == r)) - 1;
+                const int h = __shfl_sync(0xffffffffu, e, sl);
+                const int c0 = rec_i0x[h];
                 int j = lane - rec_d[h];
                 if (j < 0) j += nf;
                 tph[10] += 1;
-                const long long th0 = a.dbg ? clock64() : 0;
                 if (lane < rows && j < w) {
                   const C cw = rec_w[h];
                   const T ky = rec_ky[h * WMAX + j];
@@ -403,9 +431,10 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
                   for (int q = 0; q < WMAX; ++q)
                     if (q < w) { v[q].x += cr * kr[q]; v[q].y += ci * kr[q]; rowp[cq[q]] = v[q]; }
                 }
-                if (a.dbg) { __syncwarp(); tph[11] += clock64() - th0; }
               }
             }
+            __syncwarp();
+            if (lane == 0) seg_cnt[key] = 0;           // ready for the next chunk's fill
           }
           if (a.dbg) tph[8 + pass] += clock64() - tp0;
           __syncthreads();
