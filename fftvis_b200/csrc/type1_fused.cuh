@@ -20,6 +20,7 @@
 // their outputs through a position table.
 #pragma once
 #include <limits.h>
+#include <cuda_pipeline.h>
 
 namespace fv {
 
@@ -252,15 +253,15 @@ t1_prep_kernel(const T* __restrict__ bx, const T* __restrict__ by, const int32_t
   iy0[o] = (int)giy; zy[o] = (T)(giy - gy);
 }
 
-constexpr int T1_RC = 128;        // hit records evaluated and spread per flush chunk
+constexpr int T1_RC = 192;        // hit records evaluated and spread per flush chunk
 constexpr int T1_MAXSEG = 24;     // column segments (= warps) of the thread-per-row spreader
-constexpr int T1_SPT = 4;         // sources scanned per thread per tile (hit list holds one tile's worst case)
+constexpr int T1_SPT = 2;         // sources scanned per thread per tile (hit list holds one tile's worst case)
 
 // shared-memory bytes of pass 1 besides the strip itself
 template <typename T>
 inline size_t t1_spread_fixed_smem(int nf, int wmax, int threads) {
   return sizeof(cplx_t<T>) * nf                                    // twiddles
-         + (size_t)T1_SPT * threads * sizeof(int)                   // hit list
+         + (size_t)2 * T1_SPT * threads * sizeof(unsigned short)    // hit list (source index relative to `sbase`)
          + sizeof(int) * nf                                         // needed-column positions
          + (size_t)2 * T1_MAXSEG * (sizeof(int) + T1_RC)            // per-segment hit counters + lists
          + (size_t)T1_RC * (sizeof(cplx_t<T>) + 2 * wmax * sizeof(T) + 2 * sizeof(int));
@@ -277,7 +278,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   extern __shared__ __align__(16) unsigned char t1_smem[];
   const int w = WT > 0 ? WT : a.w;
   constexpr int WMAX = WT > 0 ? WT : kMaxW;
-  const int nthr = blockDim.x, lcap = T1_SPT * nthr;
+  const int nthr = blockDim.x, lcap = 2 * T1_SPT * nthr;
   C* strip = (C*)t1_smem;                                  // R * pitch
   C* tw = strip + (size_t)a.R * a.pitch;                   // nf
   C* rec_w = tw + a.nf;                                    // T1_RC
@@ -285,10 +286,10 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   T* rec_ky = rec_kx + T1_RC * WMAX;                       // T1_RC * WMAX
   int* rec_i0x = (int*)(rec_ky + T1_RC * WMAX);            // T1_RC
   int* rec_d = rec_i0x + T1_RC;                            // T1_RC
-  int* lst_s = rec_d + T1_RC;                              // lcap
-  int* colp = lst_s + lcap;                                // ncols (<= nf)
+  int* colp = rec_d + T1_RC;                               // ncols (<= nf)
   int* seg_cnt = colp + a.nf;                              // 2 * T1_MAXSEG: [2 * segment + straddles-its-edge]
   unsigned char* seg_list = (unsigned char*)(seg_cnt + 2 * T1_MAXSEG);   // 2 * T1_MAXSEG * T1_RC
+  unsigned short* lst_s = (unsigned short*)(seg_list + 2 * T1_MAXSEG * T1_RC);   // lcap, tile-relative
   __shared__ int hit_count;
 
   const int nf = a.nf, pitch = a.pitch;
@@ -321,6 +322,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   __syncthreads();
   T1_PHASE(0);
 
+  int sbase = 0;                                           // the hit list stores 16-bit offsets from here
   for (int tile = 0; tile < n; tile += T1_SPT * nthr) {
     // ---- scan: which sources' w-row footprints touch this strip (integer compares only) ---------
     int yv[T1_SPT];
@@ -348,18 +350,24 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
     base = __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
     for (int u = 0; u < T1_SPT; ++u) {
-      if ((ball[u] >> lane) & 1u) lst_s[base + __popc(ball[u] & ((1u << lane) - 1u))] = tile + u * nthr + tid;
+      if ((ball[u] >> lane) & 1u) lst_s[base + __popc(ball[u] & ((1u << lane) - 1u))] = (unsigned short)(tile - sbase + u * nthr + tid);
       base += __popc(ball[u]);
     }
     __syncthreads();
     const int nh = hit_count;
     T1_PHASE(1);
+    // keep scanning while another tile's worst case still fits the list and its 16-bit offsets
+    const int next = tile + T1_SPT * nthr;
+    if (next < n && nh + T1_SPT * nthr <= lcap && next + T1_SPT * nthr - sbase <= 65536) {
+      __syncthreads();                                     // everyone has read the count before it moves again
+      continue;
+    }
     tph[7] += nh;
     // ---- flush: evaluate kernels densely, then spread by row ownership -------------------------
     for (int c0 = 0; c0 < nh; c0 += T1_RC) {
       const int cn = min(T1_RC, nh - c0);
       for (int t = tid; t < 2 * cn; t += nthr) {
-        const int h = t >> 1, dim = t & 1, src = lst_s[c0 + h];
+        const int h = t >> 1, dim = t & 1, src = sbase + (int)lst_s[c0 + h];
         T z0;
         if (dim == 0) {
           z0 = zxp[src];
@@ -400,6 +408,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
             // that the sum order does not depend on the race.
             const int key = 2 * warp + pass;
             const int L = seg_cnt[key];
+            if (a.dbg && pass == 1) { tph[11] += (clock64() - tp0) + (L > 0 ? (1ll << 32) : 0); }
             for (int lb = 0; lb < L; lb += 32) {
               const int ln = min(32, L - lb);
               const int e = lane < ln ? (int)seg_list[key * T1_RC + lb + lane] : INT_MAX;
@@ -486,6 +495,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
       T1_PHASE(3);
     }
     if (tid == 0) hit_count = 0;
+    sbase = next;
     __syncthreads();
   }
 
@@ -536,11 +546,16 @@ t1_ffty_gather_kernel(T1GatherArgs<T> a) {
   const int nc = min(a.cols_per_cta, a.ncols - c0);
   const int tid = threadIdx.x;
   const C* Tb = a.Tbuf + ((int64_t)bpi * a.ncols + c0) * nf;
-  for (int i = tid; i < nc * nf; i += blockDim.x) {
-    const int ci = i / nf, rr = i - ci * nf;
-    cols[ci * pitch + rr] = Tb[i];
+  // columns -> shared memory with asynchronous copies (LDGSTS): every element's load is in flight
+  // at once instead of a register round trip per element
+  for (int ci = tid >> 5; ci < nc; ci += blockDim.x >> 5) {
+    const C* src = Tb + (int64_t)ci * nf;
+    C* dst = cols + ci * pitch;
+    for (int rr = tid & 31; rr < nf; rr += 32) __pipeline_memcpy_async(dst + rr, src + rr, sizeof(C));
   }
+  __pipeline_commit();
   for (int i = tid; i < a.st.tw_len; i += blockDim.x) tw[i] = a.tw[i];
+  __pipeline_wait_prior(0);
   __syncthreads();
   smem_fft<T>(cols, nc, pitch, nf, tw, a.st);
   __syncthreads();
