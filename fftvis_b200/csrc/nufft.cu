@@ -445,6 +445,7 @@ basis_contract_kernel(const cplx_t<T>* __restrict__ vkl, int64_t nk, const cplx_
 }  // namespace fv
 
 #include "type1_fused.cuh"
+#include "type3_tiles.cuh"
 
 // ================================================================================================
 // plan object
@@ -471,6 +472,9 @@ struct fv_plan {
   std::map<std::pair<int, int64_t>, SmemFft> smem_ffts;
   void* tbuf = nullptr; size_t tbuf_bytes = 0;   // half-transformed array T of the fused type-1 path
   void* prep = nullptr; size_t prep_bytes = 0;   // folded NU points (ix0, iy0, zx, zy) of the current batch
+  void* bins = nullptr; size_t bins_bytes = 0;   // type-3 tile lists: counts, offsets, cursor, list
+  void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+  int t3_tiles = 1;                              // 0 disables the tiled type-3 spreader
   int t1_rows = 0;                               // strip height override (0 = automatic)
   int t1_cols = 0;                               // columns per CTA override (0 = automatic)
 };
@@ -989,55 +993,102 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
   double X[3], Cc[3];
   for (int d = 0; d < dim; ++d) arraywidcen(xlim[2 * d], xlim[2 * d + 1], &X[d], &Cc[d]);
 
-  // per-frequency grids; consecutive frequencies with the same shape run as one sub-batch
-  struct Shape { int64_t nf[3]; };
-  std::vector<Shape> shp(nb);
+  // One grid shape for the whole batch: the frequencies of a batch differ by a few per cent, so the
+  // grid is sized (finufft's set_nhg_type3 rule) for the widest target extent of the batch and every
+  // frequency uses that rescaling.  Smaller extents only sit further inside the kernel's accurate
+  // range; the sources then fall on the SAME cells for every frequency (one bin sort per batch).
   std::vector<BatchParams> bp(nb);
   bool prephase = false, postphase = false;
+  double Smax[3] = {0, 0, 0};
+  std::vector<double> Dv(3 * (size_t)nb, 0.0);
+  for (int b = 0; b < nb; ++b)
+    for (int d = 0; d < dim; ++d) {
+      // targets are fl(base * scale) in working precision; min/max commute with that (monotone)
+      const double lo = (double)((T)ulim[2 * d] * (T)scale[b]), hi = (double)((T)ulim[2 * d + 1] * (T)scale[b]);
+      double S, D;
+      arraywidcen(std::min(lo, hi), std::max(lo, hi), &S, &D);
+      Smax[d] = std::max(Smax[d], S);
+      Dv[3 * (size_t)b + d] = D;
+    }
+  int64_t nf[3] = {1, 1, 1};
+  double hh[3] = {0, 0, 0}, gam[3] = {1, 1, 1};
+  for (int d = 0; d < dim; ++d) set_nhg_type3(Smax[d], X[d], upsampfac, w, &nf[d], &hh[d], &gam[d]);
   for (int b = 0; b < nb; ++b) {
     bp[b] = BatchParams{};
     bp[b].smul = 1.0;          // type 3 scales the targets (uvw = bls * freq), not the sources
     bp[b].tmul = scale[b];
-    for (int d = 0; d < 3; ++d) { shp[b].nf[d] = 1; bp[b].invgam[d] = 1.0; }
+    for (int d = 0; d < 3; ++d) bp[b].invgam[d] = 1.0;
     for (int d = 0; d < dim; ++d) {
-      // targets are fl(base * scale) in working precision; min/max commute with that (monotone)
-      const double lo = (double)((T)ulim[2 * d] * (T)scale[b]), hi = (double)((T)ulim[2 * d + 1] * (T)scale[b]);
-      double S, D, h, gam;
-      arraywidcen(std::min(lo, hi), std::max(lo, hi), &S, &D);
-      set_nhg_type3(S, X[d], upsampfac, w, &shp[b].nf[d], &h, &gam);
-      bp[b].C[d] = Cc[d]; bp[b].invgam[d] = 1.0 / gam; bp[b].D[d] = D; bp[b].hgam[d] = h * gam;
-      if (D != 0.0) prephase = true;
+      bp[b].C[d] = Cc[d]; bp[b].invgam[d] = 1.0 / gam[d]; bp[b].D[d] = Dv[3 * (size_t)b + d]; bp[b].hgam[d] = hh[d] * gam[d];
+      if (bp[b].D[d] != 0.0) prephase = true;
       if (Cc[d] != 0.0) postphase = true;
     }
   }
   rc = upload_bp(P, bp);
   if (rc) return rc;
   const Quad Q = make_quad(w, beta);
+  int64_t ng[3] = {1, 1, 1};
+  for (int d = 0; d < dim; ++d) ng[d] = next235even(std::max<int64_t>((int64_t)(upsampfac * nf[d]), 2 * w));
+  const size_t cells1 = (size_t)nf[0] * nf[1] * nf[2], cells2 = (size_t)ng[0] * ng[1] * ng[2];
+  const size_t per_b = sizeof(C) * ntr * (cells1 + cells2);
+  if (per_b > P->max_grid_bytes) { set_error("a single type-3 transform needs " + std::to_string(per_b) + " bytes of grids"); return FV_ERR_ALLOC; }
+  const int sub_max = (int)std::min<size_t>(nb, std::max<size_t>(1, P->max_grid_bytes / per_b));
+
+  // thin 3-D grids: bin-sort the sources into column tiles once for the whole batch
+  const bool tiled = dim == 3 && P->t3_tiles && nf[2] <= T3_NZMAX && n_cap > 0;
+  T3Geom<T> geo{};
+  int32_t *bin_counts = nullptr, *bin_offsets = nullptr, *bin_cursor = nullptr, *bin_list = nullptr;
+  int ntiles = 0;
+  if (tiled) {
+    geo.x = xs[0]; geo.y = xs[1]; geo.z = xs[2]; geo.n_dev = n_dev; geo.w = w;
+    for (int d = 0; d < 3; ++d) { geo.C[d] = Cc[d]; geo.invgam[d] = 1.0 / gam[d]; geo.nf[d] = (int)nf[d]; }
+    geo.ntx = ceil_div(nf[0], T3_TILE); geo.nty = ceil_div(nf[1], T3_TILE);
+    ntiles = geo.ntx * geo.nty;
+    const size_t nt1 = (size_t)ntiles + 1;
+    const size_t need = sizeof(int32_t) * (3 * nt1 + 16 * (size_t)n_cap);
+    rc = ensure(&P->bins, &P->bins_bytes, need); if (rc) return rc;
+    bin_counts = (int32_t*)P->bins; bin_offsets = bin_counts + nt1; bin_cursor = bin_offsets + nt1; bin_list = bin_cursor + nt1;
+    StageScope ts(P, FV_STAGE_ZERO);
+    FV_CUDA(cudaMemsetAsync(bin_counts, 0, sizeof(int32_t) * 3 * nt1, P->stream));
+    const int blocks = ceil_div(n_cap, 256);
+    t3_bin_kernel<T, 0><<<blocks, 256, 0, P->stream>>>(geo, bin_counts, nullptr, nullptr, nullptr);
+    FV_LAUNCH_CHECK();
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, bin_counts, bin_offsets, (int)nt1, P->stream);
+    rc = ensure(&P->scan_tmp, &P->scan_tmp_bytes, std::max<size_t>(tmp, 16)); if (rc) return rc;
+    FV_CUDA(cub::DeviceScan::ExclusiveSum(P->scan_tmp, tmp, bin_counts, bin_offsets, (int)nt1, P->stream));
+    ++fv::g_launches;
+    t3_bin_kernel<T, 1><<<blocks, 256, 0, P->stream>>>(geo, nullptr, bin_offsets, bin_cursor, bin_list);
+    FV_LAUNCH_CHECK();
+  }
 
   int b0 = 0;
   while (b0 < nb) {
-    int b1 = b0 + 1;
-    while (b1 < nb && memcmp(shp[b1].nf, shp[b0].nf, sizeof(Shape)) == 0) ++b1;
-    const int64_t* nf = shp[b0].nf;
-    int64_t ng[3] = {1, 1, 1};
-    for (int d = 0; d < dim; ++d) ng[d] = next235even(std::max<int64_t>((int64_t)(upsampfac * nf[d]), 2 * w));
-    const size_t cells1 = (size_t)nf[0] * nf[1] * nf[2], cells2 = (size_t)ng[0] * ng[1] * ng[2];
-    // cap the sub-batch so both grids fit the budget
-    int sub = b1 - b0;
-    const size_t per_b = sizeof(C) * ntr * (cells1 + cells2);
-    if (per_b > P->max_grid_bytes) { set_error("a single type-3 transform needs " + std::to_string(per_b) + " bytes of grids"); return FV_ERR_ALLOC; }
-    sub = (int)std::min<size_t>(sub, std::max<size_t>(1, P->max_grid_bytes / per_b));
-    b1 = b0 + sub;
-    rc = ensure(&P->grid, &P->grid_bytes, sizeof(C) * sub * ntr * cells1); if (rc) return rc;
-    rc = ensure(&P->grid2, &P->grid2_bytes, sizeof(C) * sub * ntr * cells2); if (rc) return rc;
-    { StageScope ts(P, FV_STAGE_ZERO); FV_CUDA(cudaMemsetAsync(P->grid, 0, sizeof(C) * sub * ntr * cells1, P->stream)); }
+    const int sub = std::min(sub_max, nb - b0);
+    const int b1 = b0 + sub;
+    rc = ensure(&P->grid, &P->grid_bytes, sizeof(C) * sub_max * ntr * cells1); if (rc) return rc;
+    rc = ensure(&P->grid2, &P->grid2_bytes, sizeof(C) * sub_max * ntr * cells2); if (rc) return rc;
+    if (tiled) {
+      T3SpreadArgs<T> ta{};
+      ta.g = geo; ta.n_cap = n_cap; ta.beta = (T)beta; ta.c = (T)(4.0 / ((double)w * w)); ta.halfw = (T)(w / 2.0);
+      ta.ntr = ntr; ta.prephase = prephase ? 1 : 0;
+      ta.W = (const C*)W + (int64_t)b0 * ntr * n_cap; ta.bp = P->bp_dev + b0;
+      ta.offsets = bin_offsets; ta.list = bin_list; ta.grid = (C*)P->grid;
+      StageScope ts(P, FV_STAGE_SPREAD);
+      dim3 tg(ntiles, sub * ntr);
+      FV_DISPATCH_W(w, (t3_col_spread_kernel<T, WT><<<tg, T3_TILE * T3_TILE, 0, P->stream>>>(ta)));
+      FV_LAUNCH_CHECK();
+    } else {
+      StageScope ts(P, FV_STAGE_ZERO);
+      FV_CUDA(cudaMemsetAsync(P->grid, 0, sizeof(C) * sub * ntr * cells1, P->stream));
+    }
 
     SpreadArgs<T> a{};
     for (int d = 0; d < 3; ++d) { a.x[d] = xs[d]; a.nf[d] = (int)nf[d]; }
     a.n_dev = n_dev; a.n_cap = n_cap; a.w = w; a.beta = (T)beta; a.c = (T)(4.0 / ((double)w * w)); a.halfw = (T)(w / 2.0);
     a.ntr = ntr; a.prephase = prephase ? 1 : 0;
     a.W = (const C*)W + (int64_t)b0 * ntr * n_cap; a.grid = (C*)P->grid; a.bp = P->bp_dev + b0;
-    rc = launch_spread<T>(P, dim, a, sub); if (rc) return rc;
+    if (!tiled) { rc = launch_spread<T>(P, dim, a, sub); if (rc) return rc; }
 
     const T *inv1, *inv2, *inv3 = nullptr;
     rc = get_invphi<T>(P, prec, nf[0], ng[0], w, beta, true, &inv1); if (rc) return rc;
@@ -1105,6 +1156,8 @@ extern "C" int fv_plan_destroy(fv_plan* P) {
   if (P->lim_dev) cudaFree(P->lim_dev);
   if (P->tbuf) cudaFree(P->tbuf);
   if (P->prep) cudaFree(P->prep);
+  if (P->bins) cudaFree(P->bins);
+  if (P->scan_tmp) cudaFree(P->scan_tmp);
   for (auto& kv : P->smem_ffts) cudaFree(kv.second.tw);
   delete P;
   return FV_OK;
@@ -1151,7 +1204,7 @@ extern "C" int fv_plan_stage_ms(fv_plan* P, int stage, double* ms_host, int64_t*
 
 extern "C" int64_t fv_plan_bytes(fv_plan* P) {
   if (!P) return 0;
-  return (int64_t)(P->grid_bytes + P->grid2_bytes + P->tbuf_bytes + P->prep_bytes + P->fft_work_bytes + P->table_bytes);
+  return (int64_t)(P->grid_bytes + P->grid2_bytes + P->tbuf_bytes + P->prep_bytes + P->bins_bytes + P->scan_tmp_bytes + P->fft_work_bytes + P->table_bytes);
 }
 
 extern "C" int fv_nufft2d1(fv_plan* plan, int prec, const void* bx, const void* by, const int32_t* n_dev,
@@ -1201,6 +1254,7 @@ extern "C" int fv_plan_set_option(fv_plan* P, const char* name, int64_t value) {
   if (n == "t1_rows") P->t1_rows = (int)value;
   else if (n == "t1_cols") P->t1_cols = (int)value;
   else if (n == "max_grid_bytes") P->max_grid_bytes = (size_t)value;
+  else if (n == "t3_tiles") P->t3_tiles = (int)value;
   else { fv::set_error("unknown option " + n); return FV_ERR_INVALID; }
   return FV_OK;
 }

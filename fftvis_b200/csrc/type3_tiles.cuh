@@ -1,0 +1,179 @@
+// Type-3 spreading (3-D, thin in z) with bin-sorted tiles and NO atomics on the grid.
+//
+// finufft's type-3 step 1 spreads every rescaled source onto w^3 cells of the fine grid
+// (finufft.nufft3d3, reference cpu/nufft.py:105-118).  A global-atomics spreader issues 2 w^3 REDs per
+// source (5500 at w = 14) and is bound by L2 atomic throughput.  Interferometer arrays are nearly
+// flat, so the z extent of the grid is the minimum 2w..32 cells: here a thread OWNS one (x, y) column
+// of the grid and keeps all of its z cells in registers.
+//
+//   t3_bin_count / t3_bin_fill   counting sort of the sources into the 16 x 16-column tiles their
+//                                footprint touches (a source lands in up to 4 lists)
+//   t3_col_spread_kernel         one CTA per (tile, frequency, product), one thread per column:
+//                                walk the tile's list; a thread whose column is inside the source's
+//                                (x, y) footprint adds W k_x k_y k_z[.] to its register column; at the
+//                                end every column is stored once (plain stores: no memset, no atomics)
+#pragma once
+#include <cub/device/device_scan.cuh>
+
+namespace fv {
+
+constexpr int T3_TILE = 16;     // columns per tile side (256 threads = one column each)
+constexpr int T3_NZMAX = 32;    // z cells a thread can hold in registers
+constexpr int T3_RS = 32;       // sources staged per round
+
+template <typename T>
+struct T3Geom {
+  const T* x; const T* y; const T* z;
+  const int32_t* n_dev;
+  double C[3], invgam[3];
+  int nf[3];
+  int w;
+  int ntx, nty;
+};
+
+template <typename T>
+__device__ __forceinline__ void t3_fold(const T3Geom<T>& g, int d, T v, int* i0w, T* z0) {
+  const double xr = ((double)v - g.C[d]) * g.invgam[d];
+  const double gg = fold_grid(xr, g.nf[d]);
+  const double gi = ceil(gg - 0.5 * (double)g.w);
+  int i0 = (int)gi;
+  if (i0 < 0) i0 += g.nf[d];
+  *i0w = i0;
+  *z0 = (T)(gi - gg);
+}
+
+// distinct tiles a w-cell footprint starting at i0w (wrapped) touches along one dimension
+__device__ __forceinline__ int t3_tiles_1d(int i0w, int w, int nf, int* out) {
+  int cnt = 0, last = -1;
+  for (int j = 0; j < w; ++j) {
+    int c = i0w + j;
+    if (c >= nf) c -= nf;
+    const int t = c / T3_TILE;
+    if (t != last) { out[cnt++] = t; last = t; }
+  }
+  return cnt;
+}
+
+// MODE 0: count list lengths; MODE 1: fill the lists (offsets from the exclusive scan of the counts)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+t3_bin_kernel(T3Geom<T> g, int32_t* __restrict__ counts, const int32_t* __restrict__ offsets,
+              int32_t* __restrict__ cursor, int32_t* __restrict__ list) {
+  const int n = *g.n_dev;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int ix, iy;
+  T zx, zy;
+  t3_fold<T>(g, 0, g.x[s], &ix, &zx);
+  t3_fold<T>(g, 1, g.y[s], &iy, &zy);
+  int tx[4], ty[4];
+  const int nx = t3_tiles_1d(ix, g.w, g.nf[0], tx), ny = t3_tiles_1d(iy, g.w, g.nf[1], ty);
+  for (int b = 0; b < ny; ++b)
+    for (int a = 0; a < nx; ++a) {
+      const int tile = ty[b] * g.ntx + tx[a];
+      if (MODE == 0) atomicAdd(&counts[tile], 1);
+      else list[offsets[tile] + atomicAdd(&cursor[tile], 1)] = s;
+    }
+}
+
+template <typename T>
+struct T3SpreadArgs {
+  T3Geom<T> g;
+  int64_t n_cap;
+  T beta, c, halfw;
+  int ntr, prephase;
+  const cplx_t<T>* W;           // (nb, ntr, n_cap)
+  const BatchParams* bp;        // D per frequency (pre-phase)
+  const int32_t* offsets;       // (ntiles + 1)
+  const int32_t* list;
+  cplx_t<T>* grid;              // (nb, ntr, nf2, nf1, nf0)
+};
+
+template <typename T, int WT>
+__global__ void __launch_bounds__(T3_TILE * T3_TILE)
+t3_col_spread_kernel(T3SpreadArgs<T> a) {
+  using C = cplx_t<T>;
+  const int w = WT > 0 ? WT : a.g.w;
+  constexpr int WMAX = WT > 0 ? WT : kMaxW;
+  __shared__ int s_ix[T3_RS], s_iy[T3_RS], s_iz[T3_RS];
+  __shared__ T s_k[3][T3_RS][WMAX];     // kernel rows of the staged sources (x, y, z)
+  __shared__ __align__(16) T s_kzr[T3_RS][T3_NZMAX];   // z row rotated onto the grid: value for cell z, 0 outside
+  __shared__ C s_w[T3_RS];
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x, ty = tile / a.g.ntx, tx = tile - ty * a.g.ntx;
+  const int bpi = blockIdx.y, b = bpi / a.ntr;
+  const int nf0 = a.g.nf[0], nf1 = a.g.nf[1], nf2 = a.g.nf[2];
+  const int gx = tx * T3_TILE + (tid & (T3_TILE - 1)), gy = ty * T3_TILE + tid / T3_TILE;
+  const bool owner = gx < nf0 && gy < nf1;
+  C acc[T3_NZMAX];
+#pragma unroll
+  for (int z = 0; z < T3_NZMAX; ++z) acc[z] = make_c<T>(T(0), T(0));
+  const int l0 = a.offsets[tile], l1 = a.offsets[tile + 1];
+  const C* Wp = a.W + (int64_t)bpi * a.n_cap;
+  const BatchParams bpar = a.bp[b];
+  for (int r0 = l0; r0 < l1; r0 += T3_RS) {
+    const int rn = min(T3_RS, l1 - r0);
+    if (tid < rn) {
+      const int s = a.list[r0 + tid];
+      const T xs = a.g.x[s], ys = a.g.y[s], zs = a.g.z[s];
+      // the first kernel argument of each dimension is parked in slot 0 until the rows are built
+      t3_fold<T>(a.g, 0, xs, &s_ix[tid], &s_k[0][tid][0]);
+      t3_fold<T>(a.g, 1, ys, &s_iy[tid], &s_k[1][tid][0]);
+      t3_fold<T>(a.g, 2, zs, &s_iz[tid], &s_k[2][tid][0]);
+      C cw = Wp[s];
+      if (a.prephase) {
+        double sn, cs;
+        sincos(bpar.D[0] * (double)xs + bpar.D[1] * (double)ys + bpar.D[2] * (double)zs, &sn, &cs);
+        cw = cmul(cw, make_c<T>((T)cs, (T)sn));
+      }
+      s_w[tid] = cw;
+    }
+    __syncthreads();
+    // kernel rows: 3 * rn * w evaluations shared by the whole CTA
+    T kv[3][(T3_RS * WMAX + T3_TILE * T3_TILE - 1) / (T3_TILE * T3_TILE)];
+#pragma unroll
+    for (int q = 0; q < (T3_RS * WMAX + T3_TILE * T3_TILE - 1) / (T3_TILE * T3_TILE); ++q) {
+      const int e = tid + q * T3_TILE * T3_TILE, rr = e / WMAX, jj = e - rr * WMAX;
+      const bool mk = rr < rn && jj < w;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) kv[d][q] = mk ? es_kernel<T>(s_k[d][rr][0] + (T)jj, a.beta, a.c, a.halfw) : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < (T3_RS * WMAX + T3_TILE * T3_TILE - 1) / (T3_TILE * T3_TILE); ++q) {
+      const int e = tid + q * T3_TILE * T3_TILE, rr = e / WMAX, jj = e - rr * WMAX;
+      if (rr < rn && jj < w) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) s_k[d][rr][jj] = kv[d][q];
+      }
+    }
+    __syncthreads();
+    // rotate the z rows onto the grid cells so that the inner loop is unconditional
+    for (int e = tid; e < rn * T3_NZMAX; e += T3_TILE * T3_TILE) {
+      const int rr = e / T3_NZMAX, z = e - rr * T3_NZMAX;
+      int jz = z - s_iz[rr]; if (jz < 0) jz += nf2;
+      s_kzr[rr][z] = (z < nf2 && jz < w) ? s_k[2][rr][jz] : T(0);
+    }
+    __syncthreads();
+    for (int r = 0; r < rn; ++r) {
+      int jx = gx - s_ix[r]; if (jx < 0) jx += nf0;
+      int jy = gy - s_iy[r]; if (jy < 0) jy += nf1;
+      if (owner && jx < w && jy < w) {
+        const T kxy = s_k[0][r][jx] * s_k[1][r][jy];
+        const C cw = s_w[r];
+        const T cr = cw.x * kxy, ci = cw.y * kxy;
+#pragma unroll
+        for (int z = 0; z < T3_NZMAX; ++z) { const T k = s_kzr[r][z]; acc[z].x += cr * k; acc[z].y += ci * k; }
+      }
+    }
+    __syncthreads();
+  }
+  if (owner) {
+    C* gp = a.grid + (int64_t)bpi * nf2 * nf1 * nf0 + (int64_t)gy * nf0 + gx;
+#pragma unroll
+    for (int z = 0; z < T3_NZMAX; ++z)
+      if (z < nf2) gp[(int64_t)z * nf1 * nf0] = acc[z];
+  }
+}
+
+}  // namespace fv
