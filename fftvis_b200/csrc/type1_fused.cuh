@@ -255,6 +255,7 @@ t1_prep_kernel(const T* __restrict__ bx, const T* __restrict__ by, const int32_t
 
 constexpr int T1_RC = 192;        // hit records evaluated and spread per flush chunk
 constexpr int T1_MAXSEG = 24;     // column segments (= warps) of the thread-per-row spreader
+constexpr int T1_SCAN = 8;        // sources per thread per scan iteration (all loads in flight together)
 constexpr int T1_SPT = 2;         // sources scanned per thread per tile (hit list holds one tile's worst case)
 
 // shared-memory bytes of pass 1 besides the strip itself
@@ -290,7 +291,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   int* seg_cnt = colp + a.nf;                              // 2 * T1_MAXSEG: [2 * segment + straddles-its-edge]
   unsigned char* seg_list = (unsigned char*)(seg_cnt + 2 * T1_MAXSEG);   // 2 * T1_MAXSEG * T1_RC
   unsigned short* lst_s = (unsigned short*)(seg_list + 2 * T1_MAXSEG * T1_RC);   // lcap, tile-relative
-  __shared__ int hit_count;
+  __shared__ int wcnt[32];
 
   const int nf = a.nf, pitch = a.pitch;
   const int bpi = blockIdx.y, b = bpi / a.ntr;
@@ -317,51 +318,60 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   for (int i = tid; i < a.R * pitch; i += nthr) strip[i] = make_c<T>(T(0), T(0));
   for (int i = tid; i < a.st.tw_len; i += nthr) tw[i] = a.tw[i];
   for (int i = tid; i < a.ncols; i += nthr) colp[i] = a.col_pos[i];
-  if (tid == 0) hit_count = 0;
   if (tid < 2 * T1_MAXSEG) seg_cnt[tid] = 0;
   __syncthreads();
   T1_PHASE(0);
 
+  // ---- which sources' w-row footprints touch this strip (integer compares on the pre-folded rows).
+  // Two passes over a range of sources: count per warp, then store at deterministic offsets (warp-major
+  // order); one barrier each instead of two per tile.  The range is everything left (up to the 16-bit
+  // offset limit) when its hits fit the list, else the worst-case-safe `lcap` sources.
+  auto is_hit = [&](int yrow) {
+    int d = yrow - r0;
+    if (d < 0) d += nf;
+    if (d < 0) d += nf;
+    return d < rows || d + w > nf;
+  };
   int sbase = 0;                                           // the hit list stores 16-bit offsets from here
-  for (int tile = 0; tile < n; tile += T1_SPT * nthr) {
-    // ---- scan: which sources' w-row footprints touch this strip (integer compares only) ---------
-    int yv[T1_SPT];
+  while (sbase < n) {
+    int shi = min(n, sbase + 65536);
+    int nh = 0, wbase = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      int cnt = 0;
+      for (int k = sbase + tid; k < shi + lane; k += T1_SCAN * nthr) {     // warp-uniform trip count
+        int yv[T1_SCAN];
 #pragma unroll
-    for (int u = 0; u < T1_SPT; ++u) {
-      const int s = tile + u * nthr + tid;
-      yv[u] = s < n ? iy0[s] : INT_MIN;
-    }
-    unsigned ball[T1_SPT];
-    int cnt = 0;
+        for (int u = 0; u < T1_SCAN; ++u) { const int s = k + u * nthr; yv[u] = s < shi ? iy0[s] : INT_MIN; }
 #pragma unroll
-    for (int u = 0; u < T1_SPT; ++u) {
-      bool hit = false;
-      if (yv[u] != INT_MIN) {
-        int d = yv[u] - r0;
-        if (d < 0) d += nf;
-        if (d < 0) d += nf;
-        hit = d < rows || d + w > nf;
+        for (int u = 0; u < T1_SCAN; ++u)
+          cnt += __popc(__ballot_sync(0xffffffffu, yv[u] != INT_MIN && is_hit(yv[u])));
       }
-      ball[u] = __ballot_sync(0xffffffffu, hit);
-      cnt += __popc(ball[u]);
+      if (lane == 0) wcnt[warp] = cnt;
+      __syncthreads();
+      nh = 0; wbase = 0;
+      for (int q = 0; q < nwarps; ++q) { const int c = wcnt[q]; nh += c; wbase += q < warp ? c : 0; }
+      __syncthreads();                                     // wcnt may be rewritten by the next attempt
+      if (nh <= lcap) break;
+      shi = min(n, sbase + lcap);                          // dense strip: take a worst-case-safe range
     }
-    int base = 0;
-    if (lane == 0 && cnt) base = atomicAdd(&hit_count, cnt);     // one reservation per warp and tile
-    base = __shfl_sync(0xffffffffu, base, 0);
+    {
+      int run = wbase;
+      for (int k = sbase + tid; k < shi + lane; k += T1_SCAN * nthr) {
+        int yv[T1_SCAN];
 #pragma unroll
-    for (int u = 0; u < T1_SPT; ++u) {
-      if ((ball[u] >> lane) & 1u) lst_s[base + __popc(ball[u] & ((1u << lane) - 1u))] = (unsigned short)(tile - sbase + u * nthr + tid);
-      base += __popc(ball[u]);
+        for (int u = 0; u < T1_SCAN; ++u) { const int s = k + u * nthr; yv[u] = s < shi ? iy0[s] : INT_MIN; }
+#pragma unroll
+        for (int u = 0; u < T1_SCAN; ++u) {
+          const bool hit = yv[u] != INT_MIN && is_hit(yv[u]);
+          const unsigned ball = __ballot_sync(0xffffffffu, hit);
+          if (hit) lst_s[run + __popc(ball & ((1u << lane) - 1u))] = (unsigned short)(k + u * nthr - sbase);
+          run += __popc(ball);
+        }
+      }
     }
     __syncthreads();
-    const int nh = hit_count;
     T1_PHASE(1);
-    // keep scanning while another tile's worst case still fits the list and its 16-bit offsets
-    const int next = tile + T1_SPT * nthr;
-    if (next < n && nh + T1_SPT * nthr <= lcap && next + T1_SPT * nthr - sbase <= 65536) {
-      __syncthreads();                                     // everyone has read the count before it moves again
-      continue;
-    }
+    const int next = shi;
     tph[7] += nh;
     // ---- flush: evaluate kernels densely, then spread by row ownership -------------------------
     for (int c0 = 0; c0 < nh; c0 += T1_RC) {
@@ -494,9 +504,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
       __syncthreads();
       T1_PHASE(3);
     }
-    if (tid == 0) hit_count = 0;
     sbase = next;
-    __syncthreads();
   }
 
   smem_fft<T>(strip, rows, pitch, nf, tw, a.st);
