@@ -58,6 +58,7 @@ class _PairTable:
     m1: torch.Tensor | None = None     # type 1: signed integer modes (flip already applied)
     m2: torch.Tensor | None = None
     modes: ModeSet | None = None       # type 1: the same modes bucketed by m1 (fused path)
+    ncols: int = 0                     # type 1: number of distinct m1 (columns the fused path keeps)
     uvw: list | None = None            # type 3: per-unit-frequency targets (flip already applied)
     ulim: list | None = None           # type 3: {min, max} of each target coordinate
 
@@ -211,12 +212,13 @@ class GPUSimulationEngine(SimulationEngine):
             rdt, cdt = _RDT[precision], _CDT[precision]
             eq_d = torch.as_tensor(eq).to(dev)
             # catalogue, frequency-major so that the gather through ascending src_idx coalesces
-            coh = np.asarray(coherency)
+            # catalogue: uploaded as given, cast and transposed to frequency-major ON the device
+            coh_d = torch.as_tensor(np.ascontiguousarray(coherency)).to(dev).to(cdt)
             if pol_sky:
-                flux_h = np.ascontiguousarray(np.transpose(coh, (1, 2, 3, 0)).reshape(nfreqs, 4, nsrc))
+                flux_d = coh_d.permute(1, 2, 3, 0).reshape(nfreqs, 4, nsrc).contiguous()
             else:
-                flux_h = np.ascontiguousarray(coh.T)
-            flux_d = torch.as_tensor(flux_h).to(dev).to(cdt)
+                flux_d = coh_d.t().contiguous()
+            del coh_d
             freqs_d = torch.as_tensor(freqs.astype(np.float64)).to(dev)
 
             order = int((beam_spline_opts or {}).get("order", 1))
@@ -258,7 +260,7 @@ class GPUSimulationEngine(SimulationEngine):
         P = 4 if polarized else 1
         fb = self.freq_batch
         if fb is None:
-            ncols = max((int(np.unique(pt.m1.cpu().numpy()).size) for pt in pairs), default=None) if is_gridded else None
+            ncols = max((pt.ncols for pt in pairs), default=None) if is_gridded else None
             fb = self._auto_batch(is_gridded, n_modes, P, precision, eps, float(upsample_factor), n_cap, ncols)
         return SimulationPlan(
             precision=precision, polarized=polarized, polarized_sky=pol_sky, nfeeds=2 if polarized else 1,
@@ -279,6 +281,7 @@ class GPUSimulationEngine(SimulationEngine):
             pt.m1 = torch.as_tensor(np.ascontiguousarray(m[0]).astype(np.int32)).to(dev)
             pt.m2 = torch.as_tensor(np.ascontiguousarray(m[1]).astype(np.int32)).to(dev)
             pt.modes = ModeSet(m[0], m[1], n_modes)
+            pt.ncols = int(np.unique(m[0]).size)
         else:
             q = np.where(fl, -bls[:, idx], bls[:, idx]).astype(rd)  # cpu_simulate.py:271
             dim = 2 if is_coplanar else 3
