@@ -475,6 +475,7 @@ struct fv_plan {
   void* bins = nullptr; size_t bins_bytes = 0;   // type-3 tile lists: counts, offsets, cursor, list
   void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
   int t3_tiles = 1;                              // 0 disables the tiled type-3 spreader
+  int t1_np4 = 0;                                // 1: spread the 4 products of a small grid in one CTA (measured slower on cfg3: off)
   int t1_rows = 0;                               // strip height override (0 = automatic)
   int t1_cols = 0;                               // columns per CTA override (0 = automatic)
 };
@@ -795,9 +796,9 @@ static int get_modeset_tables(fv_plan* P, fv_modeset* M, int prec, int64_t nf, i
   return FV_OK;
 }
 
-template <typename T, int WT>
+template <typename T, int WT, int NP>
 static int launch_t1_spread(fv_plan* P, T1SpreadArgs<T>& a, dim3 grid, int threads, size_t smem) {
-  auto kern = t1_spread_fftx_kernel<T, WT>;
+  auto kern = t1_spread_fftx_kernel<T, WT, NP>;
   FV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, threads, smem, P->stream>>>(a);
   FV_LAUNCH_CHECK();
@@ -842,18 +843,25 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   // strip height R: the whole grid when it fits one CTA, else as many rows as shared memory holds
   // (<= 32); one warp per strip row (256..768 threads): the row FFTs are warp tasks
   auto thr_for = [](int64_t rows) { return (int)std::min<int64_t>(t1_limits<T>::spread_threads, std::max<int64_t>(256, 32 * rows)); };
-  int R;
+  int R, np = 1;
+  const bool whole = t1_spread_fixed_smem<T>((int)nf, wmax, thr_for(nf)) + row_bytes * nf <= 200 * 1024;
   if (P->t1_rows > 0) R = (int)std::min<int64_t>(P->t1_rows, nf);
-  else if (t1_spread_fixed_smem<T>((int)nf, wmax, thr_for(nf)) + row_bytes * nf <= 200 * 1024) R = (int)nf;
+  else if (whole && ntr == 4 && P->t1_np4) {
+    // small grid, four polarisation products: one CTA spreads all four (shared scan / kernel
+    // evaluations / index arithmetic) on a quarter-height strip
+    np = 4;
+    R = (int)((nf + 3) / 4);
+    while (R > 1 && t1_spread_fixed_smem<T>((int)nf, wmax, thr_for(R), 4) + 4 * row_bytes * R > smem_max) --R;
+  } else if (whole) R = (int)nf;
   else {
     R = 32;
     while (R > 1 && t1_spread_fixed_smem<T>((int)nf, wmax, thr_for(R)) + row_bytes * R > smem_max) --R;
     if (R > 8) R -= R % 8;
   }
   int threads = thr_for(R);
-  size_t fixed1 = t1_spread_fixed_smem<T>((int)nf, wmax, threads);
-  while (R > 1 && fixed1 + row_bytes * R > smem_max) --R;
-  if (fixed1 + row_bytes * R > smem_max) { set_error("fine-grid row does not fit shared memory: use the cuFFT type-1 path"); return FV_ERR_UNSUPPORTED; }
+  size_t fixed1 = t1_spread_fixed_smem<T>((int)nf, wmax, threads, np);
+  while (R > 1 && fixed1 + np * row_bytes * R > smem_max) --R;
+  if (fixed1 + np * row_bytes * R > smem_max) { set_error("fine-grid row does not fit shared memory: use the cuFFT type-1 path"); return FV_ERR_UNSUPPORTED; }
   // fold every (frequency, source) point once
   const size_t per = (size_t)nb * n_cap;
   rc = ensure(&P->prep, &P->prep_bytes, per * (2 * sizeof(int32_t) + 2 * sizeof(T)));
@@ -876,8 +884,8 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   a.ncols = ncols; a.col_pos = tab->col_pos; a.Tbuf = (C*)P->tbuf;
   {
     StageScope ts(P, FV_STAGE_SPREAD);
-    dim3 grid(ceil_div(nf, R), nb * ntr);
-    const size_t smem = fixed1 + row_bytes * R;
+    dim3 grid(ceil_div(nf, R), np == 4 ? nb : nb * ntr);
+    const size_t smem = fixed1 + np * row_bytes * R;
     static const bool dbg = getenv("FV_DEBUG") != nullptr;
     static long long* dbg_dev = nullptr;
     if (dbg) {
@@ -887,7 +895,8 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
     }
     if (dbg) fprintf(stderr, "[fv] t1 fused: nf=%lld w=%d ncols=%d R=%d threads=%d smem=%zu grid=(%u,%u)\n",
                      (long long)nf, w, ncols, R, threads, smem, grid.x, grid.y);
-    FV_DISPATCH_W(w, (rc = launch_t1_spread<T, WT>(P, a, grid, threads, smem)));
+    if (np == 4) { FV_DISPATCH_W(w, (rc = launch_t1_spread<T, WT, 4>(P, a, grid, threads, smem))); }
+    else { FV_DISPATCH_W(w, (rc = launch_t1_spread<T, WT, 1>(P, a, grid, threads, smem))); }
     if (rc) return rc;
     if (dbg) {
       long long hcyc[12];
@@ -1255,6 +1264,7 @@ extern "C" int fv_plan_set_option(fv_plan* P, const char* name, int64_t value) {
   else if (n == "t1_cols") P->t1_cols = (int)value;
   else if (n == "max_grid_bytes") P->max_grid_bytes = (size_t)value;
   else if (n == "t3_tiles") P->t3_tiles = (int)value;
+  else if (n == "t1_np4") P->t1_np4 = (int)value;
   else { fv::set_error("unknown option " + n); return FV_ERR_INVALID; }
   return FV_OK;
 }

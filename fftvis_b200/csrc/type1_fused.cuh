@@ -260,19 +260,22 @@ constexpr int T1_SPT = 2;         // sources scanned per thread per tile (hit li
 
 // shared-memory bytes of pass 1 besides the strip itself
 template <typename T>
-inline size_t t1_spread_fixed_smem(int nf, int wmax, int threads) {
+inline size_t t1_spread_fixed_smem(int nf, int wmax, int threads, int np = 1) {
   return sizeof(cplx_t<T>) * nf                                    // twiddles
          + (size_t)2 * T1_SPT * threads * sizeof(unsigned short)    // hit list (source index relative to `sbase`)
          + sizeof(int) * nf                                         // needed-column positions
          + (size_t)2 * T1_MAXSEG * (sizeof(int) + T1_RC)            // per-segment hit counters + lists
-         + (size_t)T1_RC * (sizeof(cplx_t<T>) + 2 * wmax * sizeof(T) + 2 * sizeof(int));
+         + (size_t)T1_RC * (np * sizeof(cplx_t<T>) + 2 * wmax * sizeof(T) + 2 * sizeof(int));
 }
 
 template <typename T> struct t1_limits;
 template <> struct t1_limits<float> { static constexpr int spread_threads = 768, gather_blocks = 2; };
 template <> struct t1_limits<double> { static constexpr int spread_threads = 384, gather_blocks = 1; };
 
-template <typename T, int WT>
+// NP = products spread by one CTA: 1 (grid.y = frequencies x products) or 4 (grid.y = frequencies; the
+// four polarisation products share the source scan, the kernel evaluations and all index arithmetic,
+// and each keeps its own strip in shared memory).
+template <typename T, int WT, int NP>
 __global__ void __launch_bounds__(t1_limits<T>::spread_threads)
 t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   using C = cplx_t<T>;
@@ -280,10 +283,11 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   const int w = WT > 0 ? WT : a.w;
   constexpr int WMAX = WT > 0 ? WT : kMaxW;
   const int nthr = blockDim.x, lcap = 2 * T1_SPT * nthr;
-  C* strip = (C*)t1_smem;                                  // R * pitch
-  C* tw = strip + (size_t)a.R * a.pitch;                   // nf
-  C* rec_w = tw + a.nf;                                    // T1_RC
-  T* rec_kx = (T*)(rec_w + T1_RC);                         // T1_RC * WMAX
+  C* strip = (C*)t1_smem;                                  // NP * R * pitch (product-major)
+  const int pstride = a.R * a.pitch;                       // elements between the strips of two products
+  C* tw = strip + (size_t)NP * pstride;                    // nf
+  C* rec_w = tw + a.nf;                                    // T1_RC * NP
+  T* rec_kx = (T*)(rec_w + T1_RC * NP);                    // T1_RC * WMAX
   T* rec_ky = rec_kx + T1_RC * WMAX;                       // T1_RC * WMAX
   int* rec_i0x = (int*)(rec_ky + T1_RC * WMAX);            // T1_RC
   int* rec_d = rec_i0x + T1_RC;                            // T1_RC
@@ -294,7 +298,8 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   __shared__ int wcnt[32];
 
   const int nf = a.nf, pitch = a.pitch;
-  const int bpi = blockIdx.y, b = bpi / a.ntr;
+  const int bpi = NP == 1 ? blockIdx.y : blockIdx.y * a.ntr;   // index of the (first) product's transform
+  const int b = NP == 1 ? blockIdx.y / a.ntr : blockIdx.y;
   const int r0 = blockIdx.x * a.R;
   const int rows = min(a.R, nf - r0);
   const int n = *a.n_dev;
@@ -315,7 +320,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   long long tph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tc = clock64();
 #define T1_PHASE(i) do { if (a.dbg) { const long long t_ = clock64(); tph[i] += t_ - tc; tc = t_; } } while (0)
-  for (int i = tid; i < a.R * pitch; i += nthr) strip[i] = make_c<T>(T(0), T(0));
+  for (int i = tid; i < NP * pstride; i += nthr) strip[i] = make_c<T>(T(0), T(0));
   for (int i = tid; i < a.st.tw_len; i += nthr) tw[i] = a.tw[i];
   for (int i = tid; i < a.ncols; i += nthr) colp[i] = a.col_pos[i];
   if (tid < 2 * T1_MAXSEG) seg_cnt[tid] = 0;
@@ -388,7 +393,8 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
             const int key = 2 * ks + (c0w + w <= min(nf, (ks + 1) * seg) ? 0 : 1);
             seg_list[key * T1_RC + atomicAdd(&seg_cnt[key], 1)] = (unsigned char)h;
           }
-          rec_w[h] = Wp[src];
+#pragma unroll
+          for (int pp = 0; pp < NP; ++pp) rec_w[h * NP + pp] = Wp[(int64_t)pp * a.n_cap + src];
         } else {
           z0 = zyp[src];
           int d = iy0[src] - r0;
@@ -432,23 +438,25 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
                 if (j < 0) j += nf;
                 tph[10] += 1;
                 if (lane < rows && j < w) {
-                  const C cw = rec_w[h];
                   const T ky = rec_ky[h * WMAX + j];
-                  const T cr = cw.x * ky, ci = cw.y * ky;
-                  C* rowp = strip + lane * pitch;
                   const T* kx = rec_kx + h * WMAX;
-                  // all loads first, then all stores: the w cells are distinct, so the loads pipeline
                   T kr[WMAX];
-                  C v[WMAX];
                   int cq[WMAX];
 #pragma unroll
-                  for (int q = 0; q < WMAX; ++q) if (q < w) kr[q] = kx[q];
-#pragma unroll
                   for (int q = 0; q < WMAX; ++q)
-                    if (q < w) { cq[q] = pass == 0 ? c0 + q : wrap_idx(c0 + q, nf); v[q] = rowp[cq[q]]; }
+                    if (q < w) { kr[q] = kx[q] * ky; cq[q] = pass == 0 ? c0 + q : wrap_idx(c0 + q, nf); }
 #pragma unroll
-                  for (int q = 0; q < WMAX; ++q)
-                    if (q < w) { v[q].x += cr * kr[q]; v[q].y += ci * kr[q]; rowp[cq[q]] = v[q]; }
+                  for (int pp = 0; pp < NP; ++pp) {
+                    const C cw = rec_w[h * NP + pp];
+                    C* rowp = strip + pp * pstride + lane * pitch;
+                    // all loads first, then all stores: the w cells are distinct, so the loads pipeline
+                    C v[WMAX];
+#pragma unroll
+                    for (int q = 0; q < WMAX; ++q) if (q < w) v[q] = rowp[cq[q]];
+#pragma unroll
+                    for (int q = 0; q < WMAX; ++q)
+                      if (q < w) { v[q].x += cw.x * kr[q]; v[q].y += cw.y * kr[q]; rowp[cq[q]] = v[q]; }
+                  }
                 }
               }
             }
@@ -482,9 +490,11 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
             const int ja = __shfl_sync(0xffffffffu, ja_l, src_lane);
             const int jb = __shfl_sync(0xffffffffu, jb_l, src_lane);
             const int dh = __shfl_sync(0xffffffffu, dh_l, src_lane);
-            const C cw = rec_w[h];
             const T kxv = (jj < G) ? rec_kx[h * WMAX + jx] : T(0);
             const int col = wrap_idx(rec_i0x[h] + jx, nf);
+            C cw[NP];
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) cw[pp] = rec_w[h * NP + pp];
             for (int j0 = ja; j0 < jb; j0 += G) {
               const int j = j0 + jj;
               if (jj < G && j < jb) {
@@ -492,9 +502,14 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
                 if (rr >= nf) rr -= nf;
                 const T k2 = rec_ky[h * WMAX + j] * kxv;
                 C* cell = strip + rr * pitch + col;
-                C v = *cell;
-                v.x += cw.x * k2; v.y += cw.y * k2;
-                *cell = v;
+                C v[NP];
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp) v[pp] = cell[pp * pstride];
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp) {
+                  v[pp].x += cw[pp].x * k2; v[pp].y += cw[pp].y * k2;
+                  cell[pp * pstride] = v[pp];
+                }
               }
               __syncwarp();
             }
@@ -507,20 +522,25 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
     sbase = next;
   }
 
-  smem_fft<T>(strip, rows, pitch, nf, tw, a.st);
+  // rows of all products are `pitch` apart (product strips are contiguous), so one call transforms them
+  smem_fft<T>(strip, NP == 1 ? rows : NP * a.R, pitch, nf, tw, a.st);
   T1_PHASE(4);
   __syncthreads();
   T1_PHASE(5);
 
   // needed columns of this strip -> T[col][row] (rows contiguous)
-  C* Tb = a.Tbuf + (int64_t)bpi * a.ncols * nf + r0;
   const int total = a.ncols * rows;
   const unsigned inv_rows = rows > 1 ? (unsigned)(((1ull << 32) / (unsigned)rows) + 1ull) : 0u;
+#pragma unroll
+  for (int pp = 0; pp < NP; ++pp) {
+    C* Tb = a.Tbuf + (int64_t)(bpi + pp) * a.ncols * nf + r0;
+    const C* sp = strip + pp * pstride;
 #pragma unroll 4
-  for (int i = tid; i < total; i += nthr) {
-    const int ci = inv_rows ? (int)__umulhi((unsigned)i, inv_rows) : i;
-    const int rr = i - ci * rows;
-    Tb[(int64_t)ci * nf + rr] = strip[rr * pitch + colp[ci]];
+    for (int i = tid; i < total; i += nthr) {
+      const int ci = inv_rows ? (int)__umulhi((unsigned)i, inv_rows) : i;
+      const int rr = i - ci * rows;
+      Tb[(int64_t)ci * nf + rr] = sp[rr * pitch + colp[ci]];
+    }
   }
   T1_PHASE(6);
   if (a.dbg && lane == 0 && blockIdx.y == 0 && blockIdx.x < 8)
