@@ -310,7 +310,9 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   // column segments of the thread-per-row path: at least 4 w columns each, one warp per segment
   const int nseg = min(min(nwarps, T1_MAXSEG), nf / (4 * w));
   const int seg = nseg > 0 ? (nf + nseg - 1) / nseg : nf;
-  const int jj = lane / w, jx = lane - jj * w;
+  const bool use_seg = nseg >= min(nwarps, 8);             // narrow grids: row-block ownership instead
+  const int jj = lane / w, jx = lane - jj * w;              // multi-row path: (row in group, column)
+  const int jrow = lane / G, tcol = lane - jrow * G;       // segment path: (footprint row, column group)
   const int32_t* iy0 = a.iy0 + (int64_t)b * a.n_cap;
   const int32_t* ix0 = a.ix0 + (int64_t)b * a.n_cap;
   const T* zxp = a.zx + (int64_t)b * a.n_cap;
@@ -388,7 +390,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
           z0 = zxp[src];
           const int c0w = wrap_idx(ix0[src], nf);
           rec_i0x[h] = c0w;
-          if (nseg > 0) {
+          if (use_seg) {
             const int ks = c0w / seg;
             const int key = 2 * ks + (c0w + w <= min(nf, (ks + 1) * seg) ? 0 : 1);
             seg_list[key * T1_RC + atomicAdd(&seg_cnt[key], 1)] = (unsigned char)h;
@@ -409,12 +411,12 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
       }
       __syncthreads();
       T1_PHASE(2);
-      if (rows <= 32 && nseg > 0) {
-        // Thread-per-row spreading without atomics: lane = strip row, warp = column segment.  A warp
-        // walks the hits whose columns lie wholly inside its segment; every lane whose row is in the
-        // hit's footprint adds the hit's w cells of that row.  Lanes touch different rows, warps
-        // different column ranges, and a thread's own updates are program-ordered: no races, and a
-        // deterministic sum order.  Hits that straddle a segment edge (or wrap) go second, one warp.
+      if (use_seg) {
+        // Spreading without atomics: warp = column segment.  A warp walks the hits whose columns lie
+        // wholly inside its segment, one hit at a time with the hit's w x w cells spread over its
+        // lanes.  The cells of one hit are distinct, different warps own different column ranges and a
+        // warp's hits are program-ordered: no races, and a deterministic sum order.  Hits that straddle
+        // a segment edge (or wrap) go in a second pass, each by the warp of the segment they start in.
         for (int pass = 0; pass < 2; ++pass) {
           const long long tp0 = clock64();
           if (warp < nseg) {
@@ -433,29 +435,34 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
               for (int r = 0; r < ln; ++r) {
                 const int sl = __ffs(__ballot_sync(0xffffffffu, lane < ln && rank == r)) - 1;
                 const int h = __shfl_sync(0xffffffffu, e, sl);
+                // lane = (footprint row j, column group t): the hit's w x w cells are spread over
+                // w * G lanes, ceil(w / G) cells each; all cells of one hit are distinct
                 const int c0 = rec_i0x[h];
-                int j = lane - rec_d[h];
-                if (j < 0) j += nf;
+                int rr = rec_d[h] + jrow;
+                if (rr >= nf) rr -= nf;
                 tph[10] += 1;
-                if (lane < rows && j < w) {
-                  const T ky = rec_ky[h * WMAX + j];
+                if (jrow < w && rr < rows) {
+                  const T ky = rec_ky[h * WMAX + jrow];
                   const T* kx = rec_kx + h * WMAX;
-                  T kr[WMAX];
-                  int cq[WMAX];
+                  constexpr int CPL = WT > 0 ? (WT + (32 / WT) - 1) / (32 / WT) : kMaxW;   // cells per lane
+                  T kr[CPL];
+                  int cq[CPL];
 #pragma unroll
-                  for (int q = 0; q < WMAX; ++q)
-                    if (q < w) { kr[q] = kx[q] * ky; cq[q] = pass == 0 ? c0 + q : wrap_idx(c0 + q, nf); }
+                  for (int i = 0; i < CPL; ++i) {
+                    const int q = tcol + i * G;
+                    kr[i] = q < w ? kx[q] * ky : T(0);
+                    cq[i] = q < w ? (pass == 0 ? c0 + q : wrap_idx(c0 + q, nf)) : -1;
+                  }
 #pragma unroll
                   for (int pp = 0; pp < NP; ++pp) {
                     const C cw = rec_w[h * NP + pp];
-                    C* rowp = strip + pp * pstride + lane * pitch;
-                    // all loads first, then all stores: the w cells are distinct, so the loads pipeline
-                    C v[WMAX];
+                    C* rowp = strip + pp * pstride + rr * pitch;
+                    C v[CPL];
 #pragma unroll
-                    for (int q = 0; q < WMAX; ++q) if (q < w) v[q] = rowp[cq[q]];
+                    for (int i = 0; i < CPL; ++i) if (cq[i] >= 0) v[i] = rowp[cq[i]];
 #pragma unroll
-                    for (int q = 0; q < WMAX; ++q)
-                      if (q < w) { v[q].x += cw.x * kr[q]; v[q].y += cw.y * kr[q]; rowp[cq[q]] = v[q]; }
+                    for (int i = 0; i < CPL; ++i)
+                      if (cq[i] >= 0) { v[i].x += cw.x * kr[i]; v[i].y += cw.y * kr[i]; rowp[cq[i]] = v[i]; }
                   }
                 }
               }
