@@ -29,13 +29,15 @@ def _pair_table(antpos: dict, include_autos: bool):
     return keys, pos, ii[sel], jj[sel]
 
 
-def get_pos_reds(antpos, decimals=3, include_autos=True):
+def get_pos_reds(antpos, decimals=3, include_autos=True, representatives_only=False):
     """Redundant-baseline groups from antenna positions (reference core/utils.py:11-71).
 
     Groups pairs whose rounded (u, v) separation agrees up to sign (``w`` is ignored); groups
     appear in first-seen order, members in scan order, a member found with the opposite sign
     is stored reversed, and finally every group whose *first* member has ``b_y < 0`` is
-    reversed as a whole.
+    reversed as a whole.  ``representatives_only=True`` returns just the first member of every
+    group (what the engines use as the default baseline list, reference cpu_simulate.py:614-616)
+    without building the member lists.
     """
     keys, pos, i_idx, j_idx = _pair_table(antpos, include_autos)
     if i_idx.size == 0:
@@ -44,13 +46,24 @@ def get_pos_reds(antpos, decimals=3, include_autos=True):
     # canonical orientation: first non-zero component positive
     neg = (uv[:, 0] < 0) | ((uv[:, 0] == 0) & (uv[:, 1] < 0))
     canon = np.where(neg[:, None], -uv, uv) + 0.0
-    _, first, inverse = np.unique(canon, axis=0, return_index=True, return_inverse=True)
+    # group on one int64 key per pair (the separations are already rounded to `decimals`)
+    ik = np.rint(canon * 10.0**decimals).astype(np.int64)
+    key = ik[:, 0] * (np.int64(1) << 32) + (ik[:, 1] + (np.int64(1) << 31))
+    _, first, inverse = np.unique(key, return_index=True, return_inverse=True)
     inverse = inverse.reshape(-1)
     rank = np.empty(first.size, dtype=int)
     rank[np.argsort(first, kind="stable")] = np.arange(first.size)
     group_of_pair = rank[inverse]
     first_sorted = np.sort(first)
 
+    if representatives_only:
+        reps = []
+        for head in first_sorted:
+            a1, a2 = keys[i_idx[head]], keys[j_idx[head]]
+            if (pos[j_idx[head]] - pos[i_idx[head]])[1] < 0:
+                a1, a2 = a2, a1
+            reps.append((a1, a2))
+        return reps
     order = np.argsort(group_of_pair, kind="stable")
     bounds = np.searchsorted(group_of_pair[order], np.arange(first.size + 1))
     reds = []

@@ -160,7 +160,7 @@ class GPUSimulationEngine(SimulationEngine):
                 "Set polarized=True to use beam_coefs.")
         ants = {k: np.asarray(v, dtype=float) for k, v in ants.items()}
         if baselines is None:
-            baselines = [red[0] for red in core_utils.get_pos_reds(ants, include_autos=True)]
+            baselines = core_utils.get_pos_reds(ants, include_autos=True, representatives_only=True)
         baselines = [tuple(b) for b in baselines]
         nbls = len(baselines)
         coherency, pol_sky = catalog.prepare_source_catalog(np.asarray(fluxes), polarized_beam=polarized)
