@@ -52,6 +52,49 @@ __device__ inline void eval_beam(const fv_beam& b, double az, double za, double 
   const int ncomp = b.is_power ? 1 : 4;
   const int64_t plane = (int64_t)b.nza * b.naz;
   const int fi = b.freq_offset + fb;
+  if (b.order == 3) {
+    // cubic B-spline on prefiltered coefficients (scipy.ndimage.map_coordinates order=3, mode
+    // 'nearest': coordinates clamped to the original grid, coefficients of the 12-cell edge-padded
+    // grid; every tap of the 4 x 4 stencil then lies inside the padded table)
+    const int pad = b.spline_pad;
+    const int nza0 = b.nza - 2 * pad, naz0 = b.naz - 2 * pad;
+    zi = fmin(fmax(zi, 0.0), (double)(nza0 - 1)) + pad;
+    ai = fmin(fmax(ai, 0.0), (double)(naz0 - 1)) + pad;
+    const double zf = floor(zi), af = floor(ai);
+    const double tz = zi - zf, ta = ai - af;
+    double wz[4], wa[4];
+    auto bsp = [](double t, double* wgt) {
+      const double t2 = t * t, t3 = t2 * t, u = 1.0 - t;
+      wgt[0] = u * u * u / 6.0;
+      wgt[1] = (3.0 * t3 - 6.0 * t2 + 4.0) / 6.0;
+      wgt[2] = (-3.0 * t3 + 3.0 * t2 + 3.0 * t + 1.0) / 6.0;
+      wgt[3] = t3 / 6.0;
+    };
+    bsp(tz, wz); bsp(ta, wa);
+    const int zb = (int)zf - 1, ab = (int)af - 1;
+    for (int c = 0; c < ncomp; ++c) {
+      double re = 0.0, im = 0.0;
+      if (b.is_power) {
+        const typename tab_elem<T>::real* t = (const typename tab_elem<T>::real*)b.table + ((int64_t)fi) * plane;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) re += wz[i] * wa[j] * (double)t[(int64_t)(zb + i) * b.naz + ab + j];
+      } else {
+        const typename tab_elem<T>::cplx* t = (const typename tab_elem<T>::cplx*)b.table + ((int64_t)fi * 4 + c) * plane;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const auto pv = t[(int64_t)(zb + i) * b.naz + ab + j];
+            const double ww = wz[i] * wa[j];
+            re += ww * (double)pv.x; im += ww * (double)pv.y;
+          }
+      }
+      v.re[c] = re; v.im[c] = im;
+    }
+    return;
+  }
   int z0, z1, a0, a1;
   double wz, wa;
   if (b.order == 0) {
@@ -211,10 +254,12 @@ extern "C" int fv_weights(int prec, int mode, const fv_beam* beam_i_host, const 
     FV_REQUIRE(b->kind >= 0 && b->kind <= 3, "unknown beam kind");
     if (b->kind == 3) {
       FV_REQUIRE(b->table && b->nza > 0 && b->naz > 0, "table beam without table");
-      if (!(b->order == 0 || b->order == 1)) {
-        fv::set_error("beam interpolation order > 1 is not implemented on the GPU yet");
+      if (!(b->order == 0 || b->order == 1 || b->order == 3)) {
+        fv::set_error("beam interpolation order must be 0, 1 or 3");
         return FV_ERR_UNSUPPORTED;
       }
+      FV_REQUIRE(b->order != 3 || (b->spline_pad >= 2 && b->nza > 2 * b->spline_pad && b->naz > 2 * b->spline_pad),
+                 "order-3 table needs spline_pad >= 2 and a padded coefficient grid");
     }
   }
   if (nf == 0 || n_cap == 0) return FV_OK;

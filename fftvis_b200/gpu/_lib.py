@@ -22,7 +22,7 @@ class fv_beam(ctypes.Structure):
         ("kind", c_int32), ("is_power", c_int32), ("diameter", c_double), ("table", c_void_p),
         ("nza", c_int32), ("naz", c_int32), ("az_wrap_period", c_int32), ("az_pad", c_int32),
         ("az0", c_double), ("daz", c_double), ("za0", c_double), ("dza", c_double),
-        ("order", c_int32), ("freq_offset", c_int32),
+        ("order", c_int32), ("freq_offset", c_int32), ("spline_pad", c_int32), ("reserved", c_int32),
     ]
 
 

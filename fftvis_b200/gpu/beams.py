@@ -35,19 +35,38 @@ class DeviceBeam:
             self._upload_table(beam, precision, device)
 
     def _upload_table(self, beam: UVBeamTable, precision: int, device):
-        if self.desc.order not in (0, 1):
+        if self.desc.order not in (0, 1, 3):
             raise NotImplementedError(
-                "GPU beam interpolation supports spline order 0 or 1 "
-                f"(got order={self.desc.order}); pass beam_spline_opts={{'order': 1}}")
+                "GPU beam interpolation supports spline order 0, 1 or 3 "
+                f"(got order={self.desc.order}); pass beam_spline_opts={{'order': 1}} or {{'order': 3}}")
         az = np.asarray(beam.axis1_array, dtype=np.float64)
         za = np.asarray(beam.axis2_array, dtype=np.float64)
         daz, dza = az[1] - az[0], za[1] - za[0]
         data = np.asarray(beam.data_array)
         periodic = bool(np.isclose(az.size * daz, 2 * np.pi, rtol=1e-6))
         pad = 0
+        order = int(self.desc.order)
         if periodic:   # grid covers 2 pi without its end point: extend by wrapping
-            pad = 2
+            pad = max(2, order + 1)
             data = np.concatenate([data[..., -pad:], data, data[..., :pad]], axis=-1)
+        spad = 0
+        if order == 3:
+            # scipy.ndimage.map_coordinates(order=3, mode="nearest") evaluates the cubic B-spline whose
+            # coefficients are spline_filter(edge-pad(grid, 12)); the device evaluates the same
+            # coefficients (4 x 4 taps), so the prefilter runs here once per table
+            from scipy import ndimage
+            spad = 12
+            padw = [(0, 0)] * (data.ndim - 2) + [(spad, spad), (spad, spad)]
+            padded = np.pad(data, padw, mode="edge")
+            flat = padded.reshape((-1,) + padded.shape[-2:])
+            coef = np.empty(flat.shape, dtype=np.complex128 if np.iscomplexobj(flat) else np.float64)
+            for k in range(flat.shape[0]):
+                if np.iscomplexobj(flat):
+                    coef[k] = (ndimage.spline_filter(flat[k].real, order=3, output=np.float64, mode="nearest")
+                               + 1j * ndimage.spline_filter(flat[k].imag, order=3, output=np.float64, mode="nearest"))
+                else:
+                    coef[k] = ndimage.spline_filter(flat[k], order=3, output=np.float64, mode="nearest")
+            data = coef.reshape(padded.shape)
         if self.is_power:
             host = np.ascontiguousarray(np.real(data[0, 0]))                      # (nf, nza, naz)
             dt = _RDT[precision]
@@ -63,6 +82,7 @@ class DeviceBeam:
         d.nza, d.naz = int(host.shape[-2]), int(host.shape[-1])
         d.az_wrap_period = int(az.size) if periodic else 0
         d.az_pad = pad
+        d.spline_pad = spad
         d.az0, d.daz, d.za0, d.dza = float(az[0]), float(daz), float(za[0]), float(dza)
 
     def descriptor(self, freq_offset: int) -> _lib.fv_beam:

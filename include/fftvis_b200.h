@@ -89,8 +89,13 @@ typedef struct {
   int32_t az_wrap_period; /* >0: az index is taken modulo this before adding az_pad */
   int32_t az_pad;
   double az0, daz, za0, dza;
-  int32_t order;       /* interpolation order: 0 nearest, 1 bilinear */
+  int32_t order;       /* interpolation order: 0 nearest, 1 bilinear, 3 cubic B-spline (the table then
+                          holds spline COEFFICIENTS: scipy.ndimage.spline_filter of the edge-padded
+                          grid, exactly what map_coordinates(order=3, mode="nearest") evaluates) */
   int32_t freq_offset; /* table frequency index of the batch's first frequency */
+  int32_t spline_pad;  /* order 3: edge padding (12) added on every side before prefiltering; nza/naz
+                          count the padded table */
+  int32_t reserved;
 } fv_beam;
 
 /* mode: 0 unpolarised  W = sqrt(B_i B_j) F                     (cpu_simulate.py:183-186)

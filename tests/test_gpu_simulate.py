@@ -158,6 +158,24 @@ def test_evaluate_vis_chunk_slices_match_simulate():
     np.testing.assert_allclose(blk[0, :, 0, 0, :].T, full[2:5, 1], rtol=1e-12, atol=1e-12)
 
 
+def test_cubic_spline_beam_matches_cpu_pipeline():
+    """beam_spline_opts={"order": 3}: cubic B-spline interpolation of the UVBeam table (host prefilter,
+    device 4 x 4 taps) against scipy's map_coordinates inside the CPU pipeline."""
+    from fftvis_b200 import simulate_vis, synth
+    from oracle import pipeline
+    ants, flux, ra, dec, loc = _cfg1(300)
+    beam = synth.synthetic_uvbeam(FREQS, naz=72, nza=37)
+    kw = dict(precision=2, eps=1e-12, polarized=True, beam_spline_opts={"order": 3})
+    got = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beam, loc, **kw)
+    cpu = pipeline.simulate_cpu(ants, flux, ra, dec, FREQS, TIMES, [beam], loc, **kw)
+    assert relerr(got, cpu) < 1e-11
+    lin = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beam, loc, precision=2, eps=1e-12, polarized=True,
+                       beam_spline_opts={"order": 1})
+    assert 1e-6 < relerr(lin, got) < 1e-1          # the two interpolation orders genuinely differ
+    with pytest.raises(NotImplementedError):
+        simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beam, loc, polarized=True, beam_spline_opts={"order": 2})
+
+
 def test_type1_fused_and_cufft_paths_agree():
     from fftvis_b200 import AiryBeam, HERA_LOCATION, synth
     from fftvis_b200.gpu import GPUSimulationEngine

@@ -124,7 +124,7 @@ def test_coherency_golden_from_reference(golden):
     np.testing.assert_allclose(out, g["coh/out_beam_pair"], rtol=1e-12)
 
 
-@pytest.mark.parametrize("kind", ["gaussian", "airy", "table0", "table1", "table_endpoint"])
+@pytest.mark.parametrize("kind", ["gaussian", "airy", "table0", "table1", "table_endpoint", "table3", "table3_endpoint"])
 @pytest.mark.parametrize("polarized", [False, True])
 def test_evaluate_beam_vs_oracle(kind, polarized):
     from fftvis_b200 import AiryBeam, GaussianBeam, synth
@@ -142,9 +142,11 @@ def test_evaluate_beam_vs_oracle(kind, polarized):
     elif kind == "airy":
         beam = AiryBeam(diameter=14.0)
     else:
-        beam = synth.synthetic_uvbeam([freq], naz=90, nza=46, include_endpoint=(kind == "table_endpoint"))
+        beam = synth.synthetic_uvbeam([freq], naz=90, nza=46, include_endpoint=kind.endswith("endpoint"))
         if kind == "table0":
             opts = {"order": 0}
+        if kind.startswith("table3"):
+            opts = {"order": 3}
     model = beam if polarized else (beam.to_power())
     got = GPUBeamEvaluator().evaluate_beam(model, az, za, polarized, freq, spline_opts=opts)
     want = ob.evaluate_beam(model, az, za, polarized, freq, 0, opts)
