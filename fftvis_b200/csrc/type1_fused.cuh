@@ -502,24 +502,42 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
             C cw[NP];
 #pragma unroll
             for (int pp = 0; pp < NP; ++pp) cw[pp] = rec_w[h * NP + pp];
-            for (int j0 = ja; j0 < jb; j0 += G) {
-              const int j = j0 + jj;
-              if (jj < G && j < jb) {
-                int rr = dh + j;
-                if (rr >= nf) rr -= nf;
-                const T k2 = rec_ky[h * WMAX + j] * kxv;
-                C* cell = strip + rr * pitch + col;
-                C v[NP];
+            // The cells one hit touches in this warp's rows are all distinct, so up to IT row groups
+            // are loaded before the first store (the loads pipeline) and the warp only synchronises
+            // between hits.
+            constexpr int IT = NP == 1 ? 4 : 1;
+            for (int j0 = ja; j0 < jb; j0 += G * IT) {
+              C v[IT][NP];
+              C* cell[IT];
+              T k2[IT];
+              bool on[IT];
 #pragma unroll
-                for (int pp = 0; pp < NP; ++pp) v[pp] = cell[pp * pstride];
+              for (int i = 0; i < IT; ++i) {
+                const int j = j0 + i * G + jj;
+                on[i] = jj < G && j < jb;
+                cell[i] = strip;
+                k2[i] = T(0);
+                if (on[i]) {
+                  int rr = dh + j;
+                  if (rr >= nf) rr -= nf;
+                  k2[i] = rec_ky[h * WMAX + j] * kxv;
+                  cell[i] = strip + rr * pitch + col;
 #pragma unroll
-                for (int pp = 0; pp < NP; ++pp) {
-                  v[pp].x += cw[pp].x * k2; v[pp].y += cw[pp].y * k2;
-                  cell[pp * pstride] = v[pp];
+                  for (int pp = 0; pp < NP; ++pp) v[i][pp] = cell[i][pp * pstride];
                 }
               }
-              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < IT; ++i) {
+                if (on[i]) {
+#pragma unroll
+                  for (int pp = 0; pp < NP; ++pp) {
+                    v[i][pp].x += cw[pp].x * k2[i]; v[i][pp].y += cw[pp].y * k2[i];
+                    cell[i][pp * pstride] = v[i][pp];
+                  }
+                }
+              }
             }
+            __syncwarp();
           }
         }
       }

@@ -10,7 +10,7 @@ from fftvis_b200.gpu import GPUSimulationEngine
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg2"); ap.add_argument("--nfreq", type=int); ap.add_argument("--ntimes", type=int)
 ap.add_argument("--nsrc", type=int); ap.add_argument("--reps", type=int, default=2); ap.add_argument("--freq-batch", type=int)
-ap.add_argument("--force3", action="store_true"); ap.add_argument("--flo", type=int); ap.add_argument("--fhi", type=int); ap.add_argument("--precision", type=int); ap.add_argument("--eps", type=float)
+ap.add_argument("--force3", action="store_true"); ap.add_argument("--upsamp", type=float); ap.add_argument("--flo", type=int); ap.add_argument("--fhi", type=int); ap.add_argument("--precision", type=int); ap.add_argument("--eps", type=float)
 a = ap.parse_args()
 w = bench.make_workload(a.workload, a.nfreq, a.ntimes, a.nsrc)
 nbls = bench.n_baselines(w)
@@ -19,6 +19,7 @@ prec = a.precision or w["precision"]
 eng = GPUSimulationEngine(freq_batch=a.freq_batch)
 kw = dict(w["kwargs"]); kw["force_use_type3"] = a.force3
 if a.eps: kw["eps"] = a.eps
+if a.upsamp: kw["upsample_factor"] = a.upsamp
 res = {}
 for rep in range(a.reps):
     torch.cuda.synchronize(); t0 = time.perf_counter()
