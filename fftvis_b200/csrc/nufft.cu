@@ -446,6 +446,7 @@ basis_contract_kernel(const cplx_t<T>* __restrict__ vkl, int64_t nk, const cplx_
 
 #include "type1_fused.cuh"
 #include "type3_tiles.cuh"
+#include "type3_fft.cuh"
 
 // ================================================================================================
 // plan object
@@ -468,13 +469,16 @@ struct fv_plan {
   std::vector<cudaEvent_t> event_pool;
   size_t max_grid_bytes = (size_t)96 << 30;   // refuse grids beyond this (B200 has 180 GB)
   // shared-memory FFT plans of the fused type-1 path, keyed by (prec, nf)
-  struct SmemFft { fv::FftStages st; void* tw = nullptr; std::vector<int> pos; };
+  struct SmemFft { fv::FftStages st; void* tw = nullptr; std::vector<int> pos; int32_t* pos_dev = nullptr; };
   std::map<std::pair<int, int64_t>, SmemFft> smem_ffts;
   void* tbuf = nullptr; size_t tbuf_bytes = 0;   // half-transformed array T of the fused type-1 path
   void* prep = nullptr; size_t prep_bytes = 0;   // folded NU points (ix0, iy0, zx, zy) of the current batch
   void* bins = nullptr; size_t bins_bytes = 0;   // type-3 tile lists: counts, offsets, cursor, list
   void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
   int t3_tiles = 1;                              // 0 disables the tiled type-3 spreader
+  void* grid3 = nullptr; size_t grid3_bytes = 0; // intermediate of the pruned type-3 FFT passes
+  int t3_fft = 1;                                // 0: cuFFT on the padded grid; 1: own pruned shared-memory passes for 3-D
+                                                 // (where they measure faster), cuFFT for 2-D; 2: own passes always
   int t1_np4 = 0;                                // 1: spread the 4 products of a small grid in one CTA (measured slower on cfg3: off)
   int t1_rows = 0;                               // strip height override (0 = automatic)
   int t1_cols = 0;                               // columns per CTA override (0 = automatic)
@@ -1039,7 +1043,7 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
   int64_t ng[3] = {1, 1, 1};
   for (int d = 0; d < dim; ++d) ng[d] = next235even(std::max<int64_t>((int64_t)(upsampfac * nf[d]), 2 * w));
   const size_t cells1 = (size_t)nf[0] * nf[1] * nf[2], cells2 = (size_t)ng[0] * ng[1] * ng[2];
-  const size_t per_b = sizeof(C) * ntr * (cells1 + cells2);
+  const size_t per_b = sizeof(C) * ntr * (cells1 + cells2 + (dim == 3 ? (size_t)nf[2] * ng[1] * ng[0] : (size_t)nf[1] * ng[0]));
   if (per_b > P->max_grid_bytes) { set_error("a single type-3 transform needs " + std::to_string(per_b) + " bytes of grids"); return FV_ERR_ALLOC; }
   const int sub_max = (int)std::min<size_t>(nb, std::max<size_t>(1, P->max_grid_bytes / per_b));
 
@@ -1071,12 +1075,36 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
     FV_LAUNCH_CHECK();
   }
 
+  // own pruned FFT passes when every padded dimension's vectors fit shared memory
+  const size_t smem_fft_max = 200 * 1024;
+  auto vec_fit = [&](int64_t n, int cap) {
+    const int64_t room = (int64_t)smem_fft_max / (int64_t)sizeof(C) - n;      // minus the twiddle table
+    return (int)std::max<int64_t>(0, std::min<int64_t>(cap, room / (n + 1)));
+  };
+  int vx = vec_fit(ng[0], 8), vy = vec_fit(ng[1], 16), vz = dim == 3 ? vec_fit(ng[2], 64) : 1;
+  if (vy >= 4) vy -= vy % 4;
+  if (vz >= 4) vz -= vz % 4;
+  bool own_fft = (P->t3_fft == 2 || (P->t3_fft == 1 && dim == 3)) && vx >= 1 && vy >= 1 && vz >= 1;
+  fv_plan::SmemFft* F[3] = {nullptr, nullptr, nullptr};
+  if (own_fft) {
+    for (int d = 0; d < dim && own_fft; ++d) {
+      if (get_smem_fft(P, prec, ng[d], &F[d]) != FV_OK) own_fft = false;     // not 2-3-5 smooth etc.
+      else if (!F[d]->pos_dev) {
+        FV_CUDA(cudaMalloc((void**)&F[d]->pos_dev, sizeof(int) * ng[d]));
+        FV_CUDA(cudaMemcpyAsync(F[d]->pos_dev, F[d]->pos.data(), sizeof(int) * ng[d], cudaMemcpyHostToDevice, P->stream));
+        FV_CUDA(cudaStreamSynchronize(P->stream));
+      }
+    }
+  }
+  const size_t cells3 = dim == 3 ? (size_t)nf[2] * ng[1] * ng[0] : (size_t)nf[1] * ng[0];
+
   int b0 = 0;
   while (b0 < nb) {
     const int sub = std::min(sub_max, nb - b0);
     const int b1 = b0 + sub;
     rc = ensure(&P->grid, &P->grid_bytes, sizeof(C) * sub_max * ntr * cells1); if (rc) return rc;
     rc = ensure(&P->grid2, &P->grid2_bytes, sizeof(C) * sub_max * ntr * cells2); if (rc) return rc;
+    if (own_fft) { rc = ensure(&P->grid3, &P->grid3_bytes, sizeof(C) * sub_max * ntr * cells3); if (rc) return rc; }
     if (tiled) {
       T3SpreadArgs<T> ta{};
       ta.g = geo; ta.n_cap = n_cap; ta.beta = (T)beta; ta.c = (T)(4.0 / ((double)w * w)); ta.halfw = (T)(w / 2.0);
@@ -1103,16 +1131,61 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
     rc = get_invphi<T>(P, prec, nf[0], ng[0], w, beta, true, &inv1); if (rc) return rc;
     rc = get_invphi<T>(P, prec, nf[1], ng[1], w, beta, true, &inv2); if (rc) return rc;
     if (dim == 3) { rc = get_invphi<T>(P, prec, nf[2], ng[2], w, beta, true, &inv3); if (rc) return rc; }
-    {
-      StageScope ts(P, FV_STAGE_DECONV);
-      dim3 g2(ceil_div((int64_t)cells2, 256), sub * ntr);
-      if (dim == 2) deconv_pad_kernel<T, 2><<<g2, 256, 0, P->stream>>>((const C*)P->grid, (C*)P->grid2, (int)nf[0], (int)nf[1], 1, (int)ng[0], (int)ng[1], 1, inv1, inv2, inv3);
-      else deconv_pad_kernel<T, 3><<<g2, 256, 0, P->stream>>>((const C*)P->grid, (C*)P->grid2, (int)nf[0], (int)nf[1], (int)nf[2], (int)ng[0], (int)ng[1], (int)ng[2], inv1, inv2, inv3);
-      FV_LAUNCH_CHECK();
+    if (own_fft) {
+      // pruned inner FFT: deconvolve + transform x on the non-zero rows, then y, then z
+      StageScope ts(P, FV_STAGE_FFT);
+      const int q = sub * ntr;
+      C* A1 = dim == 3 ? (C*)P->grid2 : (C*)P->grid3;
+      {
+        T3FftArgs<T> fa{};
+        fa.in = (const C*)P->grid; fa.out = A1; fa.nin = (int)nf[0]; fa.n = (int)ng[0]; fa.nvec_cta = vx;
+        fa.nvec = nf[1] * nf[2]; fa.in_q = (int64_t)cells1; fa.out_q = dim == 3 ? (int64_t)cells2 : nf[1] * ng[0];
+        fa.inv1 = inv1; fa.inv2 = inv2; fa.inv3 = inv3; fa.nf2 = (int)nf[1];
+        fa.tw = (const C*)F[0]->tw; fa.st = F[0]->st; fa.pos = F[0]->pos_dev;
+        const size_t smem = sizeof(C) * ((size_t)vx * (ng[0] + 1) + ng[0]);
+        FV_CUDA(cudaFuncSetAttribute(t3_fft_contig_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 g(ceil_div(fa.nvec, vx), q);
+        t3_fft_contig_kernel<T><<<g, 512, smem, P->stream>>>(fa);
+        FV_LAUNCH_CHECK();
+      }
+      {
+        T3FftArgs<T> fa{};
+        fa.in = A1; fa.out = dim == 3 ? (C*)P->grid3 : (C*)P->grid2; fa.nin = (int)nf[1]; fa.n = (int)ng[1]; fa.nvec_cta = vy;
+        fa.ninner = (int)ng[0]; fa.nouter = (int)nf[2];
+        fa.in_q = dim == 3 ? (int64_t)cells2 : nf[1] * ng[0]; fa.in_a = nf[1] * ng[0]; fa.in_k = ng[0];
+        fa.out_q = dim == 3 ? nf[2] * ng[1] * ng[0] : (int64_t)cells2; fa.out_a = ng[1] * ng[0]; fa.out_k = ng[0];
+        fa.tw = (const C*)F[1]->tw; fa.st = F[1]->st; fa.pos = F[1]->pos_dev;
+        const size_t smem = sizeof(C) * ((size_t)vy * (ng[1] + 1) + ng[1]);
+        FV_CUDA(cudaFuncSetAttribute(t3_fft_strided_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 g((unsigned)(nf[2] * ceil_div(ng[0], vy)), q);
+        t3_fft_strided_kernel<T><<<g, 512, smem, P->stream>>>(fa);
+        FV_LAUNCH_CHECK();
+      }
+      if (dim == 3) {
+        T3FftArgs<T> fa{};
+        fa.in = (const C*)P->grid3; fa.out = (C*)P->grid2; fa.nin = (int)nf[2]; fa.n = (int)ng[2]; fa.nvec_cta = vz;
+        fa.ninner = (int)(ng[1] * ng[0]); fa.nouter = 1;
+        fa.in_q = nf[2] * ng[1] * ng[0]; fa.in_a = 0; fa.in_k = ng[1] * ng[0];
+        fa.out_q = (int64_t)cells2; fa.out_a = 0; fa.out_k = ng[1] * ng[0];
+        fa.tw = (const C*)F[2]->tw; fa.st = F[2]->st; fa.pos = F[2]->pos_dev;
+        const size_t smem = sizeof(C) * ((size_t)vz * (ng[2] + 1) + ng[2]);
+        FV_CUDA(cudaFuncSetAttribute(t3_fft_strided_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 g((unsigned)ceil_div(ng[1] * ng[0], vz), q);
+        t3_fft_strided_kernel<T><<<g, 256, smem, P->stream>>>(fa);
+        FV_LAUNCH_CHECK();
+      }
+    } else {
+      {
+        StageScope ts(P, FV_STAGE_DECONV);
+        dim3 g2(ceil_div((int64_t)cells2, 256), sub * ntr);
+        if (dim == 2) deconv_pad_kernel<T, 2><<<g2, 256, 0, P->stream>>>((const C*)P->grid, (C*)P->grid2, (int)nf[0], (int)nf[1], 1, (int)ng[0], (int)ng[1], 1, inv1, inv2, inv3);
+        else deconv_pad_kernel<T, 3><<<g2, 256, 0, P->stream>>>((const C*)P->grid, (C*)P->grid2, (int)nf[0], (int)nf[1], (int)nf[2], (int)ng[0], (int)ng[1], (int)ng[2], inv1, inv2, inv3);
+        FV_LAUNCH_CHECK();
+      }
+      cufftHandle h;
+      rc = get_fft(P, prec, dim, ng[0], ng[1], ng[2], (int64_t)sub * ntr, &h); if (rc) return rc;
+      rc = run_fft(P, h, prec, P->grid2); if (rc) return rc;
     }
-    cufftHandle h;
-    rc = get_fft(P, prec, dim, ng[0], ng[1], ng[2], (int64_t)sub * ntr, &h); if (rc) return rc;
-    rc = run_fft(P, h, prec, P->grid2); if (rc) return rc;
 
     InterpArgs<T> ia{};
     for (int d = 0; d < 3; ++d) { ia.u[d] = us[d]; ia.ng[d] = (int)ng[d]; }
@@ -1166,8 +1239,9 @@ extern "C" int fv_plan_destroy(fv_plan* P) {
   if (P->tbuf) cudaFree(P->tbuf);
   if (P->prep) cudaFree(P->prep);
   if (P->bins) cudaFree(P->bins);
+  if (P->grid3) cudaFree(P->grid3);
   if (P->scan_tmp) cudaFree(P->scan_tmp);
-  for (auto& kv : P->smem_ffts) cudaFree(kv.second.tw);
+  for (auto& kv : P->smem_ffts) { cudaFree(kv.second.tw); if (kv.second.pos_dev) cudaFree(kv.second.pos_dev); }
   delete P;
   return FV_OK;
 }
@@ -1213,7 +1287,7 @@ extern "C" int fv_plan_stage_ms(fv_plan* P, int stage, double* ms_host, int64_t*
 
 extern "C" int64_t fv_plan_bytes(fv_plan* P) {
   if (!P) return 0;
-  return (int64_t)(P->grid_bytes + P->grid2_bytes + P->tbuf_bytes + P->prep_bytes + P->bins_bytes + P->scan_tmp_bytes + P->fft_work_bytes + P->table_bytes);
+  return (int64_t)(P->grid_bytes + P->grid2_bytes + P->tbuf_bytes + P->prep_bytes + P->bins_bytes + P->grid3_bytes + P->scan_tmp_bytes + P->fft_work_bytes + P->table_bytes);
 }
 
 extern "C" int fv_nufft2d1(fv_plan* plan, int prec, const void* bx, const void* by, const int32_t* n_dev,
@@ -1265,6 +1339,7 @@ extern "C" int fv_plan_set_option(fv_plan* P, const char* name, int64_t value) {
   else if (n == "max_grid_bytes") P->max_grid_bytes = (size_t)value;
   else if (n == "t3_tiles") P->t3_tiles = (int)value;
   else if (n == "t1_np4") P->t1_np4 = (int)value;
+  else if (n == "t3_fft") P->t3_fft = (int)value;
   else { fv::set_error("unknown option " + n); return FV_ERR_INVALID; }
   return FV_OK;
 }

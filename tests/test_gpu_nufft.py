@@ -259,6 +259,48 @@ def test_type3_3d_tiled_spreader_matches_atomic_spreader_and_direct_sum(prec, ep
         assert relerr(outs[0][b], outs[1][b]) < (1e-12 if prec == 2 else 2e-5)
 
 
+@pytest.mark.parametrize("prec,dim", [(2, 2), (2, 3), (1, 2), (1, 3)])
+def test_type3_pruned_fft_matches_cufft_path(prec, dim):
+    """Inner FFT of type 3: own pruned shared-memory passes (deconvolution fused) vs cuFFT on the
+    padded grid, and both against the direct sum, on a frequency batch."""
+    import torch
+    from fftvis_b200.gpu import _lib
+    from fftvis_b200.gpu.nufft import default_plan
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(40 + dim)
+    n, nk, nb, ntr = 4000, 257, 2, 2
+    rd, cd = _types(prec)
+    rdt, cdt = (torch.float32, torch.complex64) if prec == 1 else (torch.float64, torch.complex128)
+    eps = 6e-8 if prec == 1 else 1e-12
+    lm = rng.uniform(-0.7, 0.7, (2, n))
+    x = [(2 * np.pi * v).astype(rd) for v in (lm[0], lm[1], np.sqrt(1 - (lm**2).sum(0)))][:dim]
+    u = [rng.uniform(-2e-7, 3e-7, nk).astype(rd), rng.uniform(-3e-7, 3e-7, nk).astype(rd),
+         rng.uniform(-5e-9, 5e-9, nk).astype(rd)][:dim]
+    scale = np.array([1.0e8, 1.3e8])
+    W = (rng.normal(size=(nb, ntr, n)) + 1j * rng.normal(size=(nb, ntr, n))).astype(cd)
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dt)
+    xs, us, Wd = [t(a, rdt) for a in x], [t(a, rdt) for a in u], t(W, cdt)
+    if dim == 2:
+        xs, us = xs + [xs[0]], us + [us[0]]          # placeholders (ignored for dim = 2)
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
+    plan = default_plan()
+    outs = []
+    for own in (2, 0):
+        plan.set_option("t3_fft", own)
+        out = torch.zeros((nb, ntr, nk), dtype=cdt, device="cuda")
+        epi = _lib.make_epilogue(out.data_ptr(), out.stride(0), out.stride(1))
+        plan.type3(prec, dim, xs, n_dev, None, us, None, scale, Wd, eps, 2.0, epi)
+        outs.append(out.cpu().numpy())
+    plan.set_option("t3_fft", 1)
+    for b in range(nb):
+        uu = [(a * rd(scale[b])).astype(rd) for a in u]
+        want = nc.direct_sum(x[0], x[1], x[2] if dim == 3 else None, W[b], uu[0], uu[1], uu[2] if dim == 3 else None)
+        tol = 10 * eps if prec == 2 else 5e-5
+        assert relerr(outs[0][b], want) < tol
+        assert relerr(outs[1][b], want) < tol
+        assert relerr(outs[0][b], outs[1][b]) < (1e-12 if prec == 2 else 2e-5)
+
+
 def test_epilogue_conj_kmap_pmap_accumulate():
     import torch
     from fftvis_b200.gpu import _lib
