@@ -479,6 +479,7 @@ struct fv_plan {
   void* grid3 = nullptr; size_t grid3_bytes = 0; // intermediate of the pruned type-3 FFT passes
   int t3_fft = 1;                                // 0: cuFFT on the padded grid; 1: own pruned shared-memory passes for 3-D
                                                  // (where they measure faster), cuFFT for 2-D; 2: own passes always
+  int t3_v[3] = {0, 0, 0}, t3_thr[3] = {0, 0, 0}; // tuning overrides: vectors per CTA / threads of the x, y, z passes
   int t1_np4 = 0;                                // 1: spread the 4 products of a small grid in one CTA (measured slower on cfg3: off)
   int t1_rows = 0;                               // strip height override (0 = automatic)
   int t1_cols = 0;                               // columns per CTA override (0 = automatic)
@@ -1084,6 +1085,11 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
   int vx = vec_fit(ng[0], 8), vy = vec_fit(ng[1], 16), vz = dim == 3 ? vec_fit(ng[2], 64) : 1;
   if (vy >= 4) vy -= vy % 4;
   if (vz >= 4) vz -= vz % 4;
+  if (P->t3_v[0] > 0) vx = std::min(vx, P->t3_v[0]);
+  if (P->t3_v[1] > 0) vy = std::min(vy, P->t3_v[1]);
+  if (P->t3_v[2] > 0) vz = std::min(vz, P->t3_v[2]);
+  const int thx = P->t3_thr[0] > 0 ? P->t3_thr[0] : 512, thy = P->t3_thr[1] > 0 ? P->t3_thr[1] : 512,
+            thz = P->t3_thr[2] > 0 ? P->t3_thr[2] : 256;
   bool own_fft = (P->t3_fft == 2 || (P->t3_fft == 1 && dim == 3)) && vx >= 1 && vy >= 1 && vz >= 1;
   fv_plan::SmemFft* F[3] = {nullptr, nullptr, nullptr};
   if (own_fft) {
@@ -1145,7 +1151,7 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
         const size_t smem = sizeof(C) * ((size_t)vx * (ng[0] + 1) + ng[0]);
         FV_CUDA(cudaFuncSetAttribute(t3_fft_contig_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 g(ceil_div(fa.nvec, vx), q);
-        t3_fft_contig_kernel<T><<<g, 512, smem, P->stream>>>(fa);
+        t3_fft_contig_kernel<T><<<g, thx, smem, P->stream>>>(fa);
         FV_LAUNCH_CHECK();
       }
       {
@@ -1158,7 +1164,7 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
         const size_t smem = sizeof(C) * ((size_t)vy * (ng[1] + 1) + ng[1]);
         FV_CUDA(cudaFuncSetAttribute(t3_fft_strided_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 g((unsigned)(nf[2] * ceil_div(ng[0], vy)), q);
-        t3_fft_strided_kernel<T><<<g, 512, smem, P->stream>>>(fa);
+        t3_fft_strided_kernel<T><<<g, thy, smem, P->stream>>>(fa);
         FV_LAUNCH_CHECK();
       }
       if (dim == 3) {
@@ -1171,7 +1177,7 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
         const size_t smem = sizeof(C) * ((size_t)vz * (ng[2] + 1) + ng[2]);
         FV_CUDA(cudaFuncSetAttribute(t3_fft_strided_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 g((unsigned)ceil_div(ng[1] * ng[0], vz), q);
-        t3_fft_strided_kernel<T><<<g, 256, smem, P->stream>>>(fa);
+        t3_fft_strided_kernel<T><<<g, thz, smem, P->stream>>>(fa);
         FV_LAUNCH_CHECK();
       }
     } else {
@@ -1340,6 +1346,8 @@ extern "C" int fv_plan_set_option(fv_plan* P, const char* name, int64_t value) {
   else if (n == "t3_tiles") P->t3_tiles = (int)value;
   else if (n == "t1_np4") P->t1_np4 = (int)value;
   else if (n == "t3_fft") P->t3_fft = (int)value;
+  else if (n.rfind("t3_v", 0) == 0 && n.size() == 5 && n[4] >= 'x' && n[4] <= 'z') P->t3_v[n[4] - 'x'] = (int)value;
+  else if (n.rfind("t3_thr", 0) == 0 && n.size() == 7 && n[6] >= 'x' && n[6] <= 'z') P->t3_thr[n[6] - 'x'] = (int)value;
   else { fv::set_error("unknown option " + n); return FV_ERR_INVALID; }
   return FV_OK;
 }

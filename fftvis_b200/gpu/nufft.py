@@ -58,7 +58,9 @@ class NufftPlan:
             h = ctypes.c_void_p()
             _lib.check(_lib.lib().fv_plan_create(ctypes.byref(h), self.stream.cuda_stream), "fv_plan_create")
         self._h = h
-        for env, opt in (("FV_T1_ROWS", "t1_rows"), ("FV_T1_COLS", "t1_cols")):   # tuning experiments
+        for env, opt in (("FV_T1_ROWS", "t1_rows"), ("FV_T1_COLS", "t1_cols"), ("FV_T3_VX", "t3_vx"),
+                         ("FV_T3_VY", "t3_vy"), ("FV_T3_VZ", "t3_vz"), ("FV_T3_THRX", "t3_thrx"),
+                         ("FV_T3_THRY", "t3_thry"), ("FV_T3_THRZ", "t3_thrz")):   # tuning experiments
             if os.environ.get(env):
                 self.set_option(opt, int(os.environ[env]))
 
