@@ -14,6 +14,7 @@
 //                                end every column is stored once (plain stores: no memset, no atomics)
 #pragma once
 #include <cub/device/device_scan.cuh>
+#include <type_traits>
 
 namespace fv {
 
@@ -162,8 +163,15 @@ t3_col_spread_kernel(T3SpreadArgs<T> a) {
         const T kxy = s_k[0][r][jx] * s_k[1][r][jy];
         const C cw = s_w[r];
         const T cr = cw.x * kxy, ci = cw.y * kxy;
+        // two z cells per shared-memory load (the row is 16-byte aligned and read as a broadcast)
+        using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+        const T2* kz2 = reinterpret_cast<const T2*>(&s_kzr[r][0]);
 #pragma unroll
-        for (int z = 0; z < T3_NZMAX; ++z) { const T k = s_kzr[r][z]; acc[z].x += cr * k; acc[z].y += ci * k; }
+        for (int z = 0; z < T3_NZMAX; z += 2) {
+          const T2 k = kz2[z >> 1];
+          acc[z].x += cr * k.x; acc[z].y += ci * k.x;
+          acc[z + 1].x += cr * k.y; acc[z + 1].y += ci * k.y;
+        }
       }
     }
     __syncthreads();
