@@ -322,7 +322,13 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   long long tph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tc = clock64();
 #define T1_PHASE(i) do { if (a.dbg) { const long long t_ = clock64(); tph[i] += t_ - tc; tc = t_; } } while (0)
-  for (int i = tid; i < NP * pstride; i += nthr) strip[i] = make_c<T>(T(0), T(0));
+  {
+    // clear the strip with 16-byte stores
+    const int n16 = (int)(((size_t)NP * pstride * sizeof(C)) / 16);
+    int4* z4 = reinterpret_cast<int4*>(strip);
+    for (int i = tid; i < n16; i += nthr) z4[i] = make_int4(0, 0, 0, 0);
+    for (int i = n16 * (16 / (int)sizeof(C)) + tid; i < NP * pstride; i += nthr) strip[i] = make_c<T>(T(0), T(0));
+  }
   for (int i = tid; i < a.st.tw_len; i += nthr) tw[i] = a.tw[i];
   for (int i = tid; i < a.ncols; i += nthr) colp[i] = a.col_pos[i];
   if (tid < 2 * T1_MAXSEG) seg_cnt[tid] = 0;
@@ -343,25 +349,48 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   while (sbase < n) {
     int shi = min(n, sbase + 65536);
     int nh = 0, wbase = 0;
+    // the common case: the whole range is one scan iteration, whose rows stay in registers between
+    // the count pass and the store pass (no second trip to global memory)
+    const bool single = shi - sbase <= T1_SCAN * nthr;
+    unsigned hits_u = 0;                                   // single: bit u = my source u is a hit
     for (int attempt = 0; attempt < 2; ++attempt) {
       int cnt = 0;
       for (int k = sbase + tid; k < shi + lane; k += T1_SCAN * nthr) {     // warp-uniform trip count
         int yv[T1_SCAN];
 #pragma unroll
         for (int u = 0; u < T1_SCAN; ++u) { const int s = k + u * nthr; yv[u] = s < shi ? iy0[s] : INT_MIN; }
+        hits_u = 0;
 #pragma unroll
-        for (int u = 0; u < T1_SCAN; ++u)
-          cnt += __popc(__ballot_sync(0xffffffffu, yv[u] != INT_MIN && is_hit(yv[u])));
+        for (int u = 0; u < T1_SCAN; ++u) {
+          const bool hit = yv[u] != INT_MIN && is_hit(yv[u]);
+          hits_u |= hit ? (1u << u) : 0u;
+          cnt += __popc(__ballot_sync(0xffffffffu, hit));
+        }
       }
       if (lane == 0) wcnt[warp] = cnt;
       __syncthreads();
-      nh = 0; wbase = 0;
-      for (int q = 0; q < nwarps; ++q) { const int c = wcnt[q]; nh += c; wbase += q < warp ? c : 0; }
+      {
+        // totals and this warp's base by a shuffle scan over the per-warp counts
+        int c = lane < nwarps ? wcnt[lane] : 0, inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        nh = __shfl_sync(0xffffffffu, inc, 31);
+        wbase = __shfl_sync(0xffffffffu, inc - c, warp);
+      }
       __syncthreads();                                     // wcnt may be rewritten by the next attempt
       if (nh <= lcap) break;
       shi = min(n, sbase + lcap);                          // dense strip: take a worst-case-safe range
     }
-    {
+    if (single && shi - sbase <= T1_SCAN * nthr && nh <= lcap && (shi == min(n, sbase + 65536))) {
+      int run = wbase;
+#pragma unroll
+      for (int u = 0; u < T1_SCAN; ++u) {
+        const bool hit = (hits_u >> u) & 1u;
+        const unsigned ball = __ballot_sync(0xffffffffu, hit);
+        if (hit) lst_s[run + __popc(ball & ((1u << lane) - 1u))] = (unsigned short)(tid + u * nthr);
+        run += __popc(ball);
+      }
+    } else {
       int run = wbase;
       for (int k = sbase + tid; k < shi + lane; k += T1_SCAN * nthr) {
         int yv[T1_SCAN];
