@@ -494,6 +494,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
                       if (cq[i] >= 0) { v[i].x += cw.x * kr[i]; v[i].y += cw.y * kr[i]; rowp[cq[i]] = v[i]; }
                   }
                 }
+                __syncwarp();                              // the next hit may touch the same cells from other lanes
               }
             }
             __syncwarp();
