@@ -166,7 +166,7 @@ def get_desired_chunks(freemem, min_chunks, beam_list, nax, nfeed, nant, nsrc, p
     )
     need = get_required_chunks(freemem, nax, nfeed, nant, nsrc, len(beam_list), nbeampix,
                                precision, source_buffer)
-    nchunks = min(max(min_chunks, need), nsrc)
+    nchunks = max(1, min(max(min_chunks, need), nsrc))     # (the reference divides by zero on an empty sky)
     return nchunks, int(np.ceil(nsrc / nchunks))
 
 

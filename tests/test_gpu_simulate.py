@@ -208,6 +208,44 @@ def test_f32_close_to_f64_and_no_sources_above_horizon():
     assert np.all(out == 0)
 
 
+@pytest.mark.parametrize("force3", [False, True])
+def test_polarized_analytic_and_uniform_beams(force3):
+    from fftvis_b200 import AiryBeam, UniformBeam, simulate_vis
+    from oracle import pipeline
+    ants, flux, ra, dec, loc = _cfg1(150)
+    for beam in (AiryBeam(diameter=14.0), UniformBeam()):
+        kw = dict(precision=2, eps=1e-12, polarized=True, force_use_type3=force3)
+        got = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beam, loc, **kw)
+        cpu = pipeline.simulate_cpu(ants, flux, ra, dec, FREQS, TIMES, [beam], loc, **kw)
+        assert relerr(got, cpu) < 1e-11
+        # an unpolarised analytic beam gives identical xx / yy and identical cross products
+        np.testing.assert_allclose(got[:, :, 0, 0], got[:, :, 1, 1], rtol=1e-12, atol=1e-12)
+
+
+def test_degenerate_inputs():
+    """Autos only (zero-length baselines), a single source, one antenna, and an empty sky."""
+    from fftvis_b200 import GaussianBeam, HERA_LOCATION, simulate_vis
+    from oracle import pipeline
+    beam = GaussianBeam(diameter=14.0)
+    ants = {0: np.array([0.0, 0.0, 0.0]), 5: np.array([14.6, 0.0, 0.0])}
+    ra, dec, flux = small_sky(50, FREQS)
+    autos = [(0, 0), (5, 5)]
+    got = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beam, HERA_LOCATION, baselines=autos, precision=2)
+    ref = pipeline.simulate_direct(ants, flux, ra, dec, FREQS, TIMES, [beam.to_power()], HERA_LOCATION,
+                                   baselines=autos, precision=2)
+    assert relerr(got, ref) < 1e-11 and np.abs(got.imag).max() < 1e-9 * np.abs(got.real).max()
+    one = {7: np.array([1.0, 2.0, 0.0])}
+    got = simulate_vis(one, flux, ra, dec, FREQS, TIMES, beam, HERA_LOCATION, precision=2)
+    ref = pipeline.simulate_direct(one, flux, ra, dec, FREQS, TIMES, [beam.to_power()], HERA_LOCATION, precision=2)
+    assert got.shape == ref.shape == (2, 2, 1) and relerr(got, ref) < 1e-11
+    got = simulate_vis(ants, flux[:1], ra[:1], dec[:1], FREQS, TIMES, beam, HERA_LOCATION, precision=2)
+    ref = pipeline.simulate_direct(ants, flux[:1], ra[:1], dec[:1], FREQS, TIMES, [beam.to_power()], HERA_LOCATION,
+                                   precision=2)
+    assert relerr(got, ref) < 1e-11 or np.all(ref == 0)
+    empty = simulate_vis(ants, flux[:0], ra[:0], dec[:0], FREQS, TIMES, beam, HERA_LOCATION, precision=2)
+    assert empty.shape[:2] == (2, 2) and np.all(empty == 0)
+
+
 def test_wrapper_errors_match_reference_strings():
     """reference tests/test_wrapper.py:123-141, tests/test_beam_basis.py:459,476."""
     from fftvis_b200 import GaussianBeam, HERA_LOCATION, simulate_vis
