@@ -73,6 +73,23 @@ def make_workload(name: str, nfreq=None, ntimes=None, nsrc=None, time_block: int
                       "(3.1M pixels, ~1.5M above horizon), 512 freqs, f64")
         freqs = np.linspace(100e6, 200e6, nfreq)
         sky = synth.random_sky(nsrc, freqs, seed=42, kind="diffuse")
+    elif name == "cfg5":
+        nfreq, ntimes, nsrc = nfreq or 1024, ntimes or 120, nsrc or 100000
+        freqs = np.linspace(100e6, 200e6, nfreq)
+        ants = synth.hex_array(7)
+        ants[len(ants)] = np.array([7 * synth.HEX_SPACING, 0.0, 0.0])          # 127 + 1 antennas, on the lattice
+        K = 5
+        basis = [synth.synthetic_uvbeam(freqs, naz=360, nza=181, seed=s, perturb=0.3) for s in range(K)]
+        for b in basis:
+            b.data_array = b.data_array.real.astype(complex)      # real basis beams (reference's upper-triangle trick)
+        rng = np.random.default_rng(42)
+        coefs = rng.normal(size=(len(ants), K, nfreq)) + 1j * rng.normal(size=(len(ants), K, nfreq))
+        w.update(ants=ants, beam=basis, precision=2, polarized=True,
+                 kwargs=dict(baselines=synth.all_baselines(ants, autos=True), beam_coefs=coefs,
+                             beam_spline_opts={"order": 1}),
+                 desc="per-antenna beams via 5-term beam-basis decomposition, 128 antennas, polarized, 100k "
+                      "sources, 1024 freqs x 120 times")
+        sky = synth.random_sky(nsrc, freqs, seed=42, kind="gleam")
     else:
         raise SystemExit(f"unknown workload {name}")
     t0 = START_JD + time_block * ntimes * CADENCE_S / 86400.0
@@ -155,12 +172,13 @@ def cpu_sample(w, nbls, budget_s: float = 15.0):
     # regions take an explicit thread count
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     beam = w["beam"] if w["polarized"] else w["beam"].to_power()
+    beam_list = beam if isinstance(beam, list) else [beam]
     base = dict(precision=w["precision"], polarized=w["polarized"], nthreads=cores, **w["kwargs"])
 
     def run(nf, nt):
         fs = slice(0, nf)
         t0 = time.perf_counter()
-        pipeline.simulate_cpu(w["ants"], w["fluxes"], w["ra"], w["dec"], w["freqs"], w["times"], [beam],
+        pipeline.simulate_cpu(w["ants"], w["fluxes"], w["ra"], w["dec"], w["freqs"], w["times"], beam_list,
                               w["telescope_loc"], freq_slice=fs, time_slice=slice(0, nt), **base)
         return time.perf_counter() - t0
 
@@ -249,8 +267,9 @@ def run_gpu(args):
     w = make_workload(args.workload, args.nfreq, args.ntimes, args.nsrc, time_block=rank)
     nbls = n_baselines(w)
     beam = w["beam"] if w["polarized"] else w["beam"].to_power()
+    beam_list = beam if isinstance(beam, list) else [beam]
     eng = GPUSimulationEngine(freq_batch=args.freq_batch, type1_method=args.type1_method)
-    plan = eng.prepare(w["ants"], w["freqs"], w["fluxes"], [beam], w["ra"], w["dec"], w["times"],
+    plan = eng.prepare(w["ants"], w["freqs"], w["fluxes"], beam_list, w["ra"], w["dec"], w["times"],
                        w["telescope_loc"], precision=w["precision"], polarized=w["polarized"], **w["kwargs"])
     P = 4 if plan.polarized else 1
     out = torch.zeros((plan.nf_local, plan.ntimes, P, plan.nbls),
@@ -326,7 +345,7 @@ def run_gpu(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         eng2 = GPUSimulationEngine(freq_batch=args.freq_batch, type1_method=args.type1_method)
-        plan2 = eng2.prepare(w["ants"], w["freqs"], w["fluxes"], [beam], w["ra"], w["dec"], w["times"][:1],
+        plan2 = eng2.prepare(w["ants"], w["freqs"], w["fluxes"], beam_list, w["ra"], w["dec"], w["times"][:1],
                              w["telescope_loc"], precision=w["precision"], polarized=w["polarized"], **w["kwargs"])
         # mean number of live (above-horizon) sources, for the algorithmic byte count
         n_live = 0.5 * w["nsrc"]

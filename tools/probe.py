@@ -15,6 +15,7 @@ a = ap.parse_args()
 w = bench.make_workload(a.workload, a.nfreq, a.ntimes, a.nsrc)
 nbls = bench.n_baselines(w)
 beam = w["beam"] if w["polarized"] else w["beam"].to_power()
+beam_list = beam if isinstance(beam, list) else [beam]
 prec = a.precision or w["precision"]
 eng = GPUSimulationEngine(freq_batch=a.freq_batch)
 kw = dict(w["kwargs"]); kw["force_use_type3"] = a.force3
@@ -23,7 +24,7 @@ if a.upsamp: kw["upsample_factor"] = a.upsamp
 res = {}
 for rep in range(a.reps):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    plan = eng.prepare(w["ants"], w["freqs"], w["fluxes"], [beam], w["ra"], w["dec"], w["times"], w["telescope_loc"],
+    plan = eng.prepare(w["ants"], w["freqs"], w["fluxes"], beam_list, w["ra"], w["dec"], w["times"], w["telescope_loc"],
                        precision=prec, polarized=w["polarized"],
                        freq_range=(a.flo, a.fhi) if a.fhi else None, **kw)
     torch.cuda.synchronize(); t1 = time.perf_counter()
