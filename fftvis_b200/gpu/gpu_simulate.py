@@ -305,7 +305,7 @@ class GPUSimulationEngine(SimulationEngine):
             by_grid = max(1, self.grid_budget_bytes // max(P * nf * nf * csize, 1))
             return int(max(1, min(256, by_grid, by_w)))
         per_f = P * (ncols or n_modes) * nf * csize
-        nb_max = int(max(1, min(64, by_w, (96 << 20) // max(per_f, 1))))
+        nb_max = int(max(1, min(128, by_w, (96 << 20) // max(per_f, 1))))
         row_bytes = (nf + 1) * csize
         if row_bytes * nf <= 160 * 1024:
             strips = 1
