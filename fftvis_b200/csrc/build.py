@@ -13,7 +13,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 LIB = HERE.parent / "libfftvis_b200.so"
-SOURCES = ["api.cu", "rotate_cut.cu", "weights.cu", "nufft.cu"]
+SOURCES = ["api.cu", "rotate_cut.cu", "weights.cu", "nufft.cu", "type1_fused.cu", "type3.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

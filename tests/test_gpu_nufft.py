@@ -107,35 +107,6 @@ def test_type1_fused_grid_sizes_and_strip_heights(n_modes, rows, prec):
         assert relerr(got, want) < max(3 * relerr(ref, want), 3e-5)
 
 
-@pytest.mark.parametrize("prec,n_modes", [(2, 41), (1, 41), (2, 7), (1, 91)])
-def test_type1_fused_four_products_in_one_cta(prec, n_modes):
-    """Small grids with four polarisation products: optionally one CTA spreads all four (shared scan
-    and kernel evaluations; opt-in, it measured slower on cfg3).  Must equal the one-product-per-CTA
-    form and the direct sum."""
-    from fftvis_b200.gpu import gpu_nufft2d_type1
-    from fftvis_b200.gpu.nufft import default_plan
-    from oracle import nufft_cpu as nc
-    rng = np.random.default_rng(77 + n_modes)
-    n, nk = 5000, 300
-    rd, cd = _types(prec)
-    eps = 6e-8 if prec == 1 else 1e-13
-    x = rng.uniform(-60, 60, n).astype(rd)
-    y = rng.uniform(-60, 60, n).astype(rd)
-    c = (rng.normal(size=(4, n)) + 1j * rng.normal(size=(4, n))).astype(cd)
-    h = n_modes // 2
-    idx = rng.integers(-h, h + 1, size=(2, nk))
-    plan = default_plan()
-    got = {}
-    for np4 in (1, 0):
-        plan.set_option("t1_np4", np4)
-        got[np4] = gpu_nufft2d_type1(x, y, c, n_modes, idx, eps, method="fused")
-    plan.set_option("t1_np4", 0)
-    want = nc.direct_sum(x, y, None, c, idx[0], idx[1], None)
-    tol = 10 * eps if prec == 2 else 5e-5
-    assert relerr(got[1], want) < tol and relerr(got[0], want) < tol
-    assert relerr(got[1], got[0]) < (1e-13 if prec == 2 else 1e-5)
-
-
 def test_type3_offcentre_points_and_targets():
     """Non-zero centres exercise the pre- and post-phases."""
     from fftvis_b200.gpu import gpu_nufft3d
