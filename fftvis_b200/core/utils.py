@@ -49,6 +49,14 @@ def get_pos_reds(antpos, decimals=3, include_autos=True, representatives_only=Fa
     # group on one int64 key per pair (the separations are already rounded to `decimals`)
     ik = np.rint(canon * 10.0**decimals).astype(np.int64)
     key = ik[:, 0] * (np.int64(1) << 32) + (ik[:, 1] + (np.int64(1) << 31))
+    if representatives_only:
+        _, first = np.unique(key, return_index=True)
+        first_sorted = np.sort(first)
+        hi, hj = i_idx[first_sorted], j_idx[first_sorted]
+        swap = (pos[hj, 1] - pos[hi, 1]) < 0
+        a1 = np.where(swap, hj, hi).tolist()
+        a2 = np.where(swap, hi, hj).tolist()
+        return [(keys[p], keys[q]) for p, q in zip(a1, a2)]
     _, first, inverse = np.unique(key, return_index=True, return_inverse=True)
     inverse = inverse.reshape(-1)
     rank = np.empty(first.size, dtype=int)
@@ -56,14 +64,6 @@ def get_pos_reds(antpos, decimals=3, include_autos=True, representatives_only=Fa
     group_of_pair = rank[inverse]
     first_sorted = np.sort(first)
 
-    if representatives_only:
-        reps = []
-        for head in first_sorted:
-            a1, a2 = keys[i_idx[head]], keys[j_idx[head]]
-            if (pos[j_idx[head]] - pos[i_idx[head]])[1] < 0:
-                a1, a2 = a2, a1
-            reps.append((a1, a2))
-        return reps
     order = np.argsort(group_of_pair, kind="stable")
     bounds = np.searchsorted(group_of_pair[order], np.arange(first.size + 1))
     reds = []

@@ -24,3 +24,17 @@ extern "C" int fv_device_count(int* count_host) {
   *count_host = n;
   return FV_OK;
 }
+
+// Strided copy between host and device on `stream` (cudaMemcpy2DAsync).  The engine streams each
+// finished time slab of the (nf, nt, P, nbls) visibility array into the caller's page-locked result
+// while later time steps are still being computed.  direction: 0 = device -> host, 1 = host -> device.
+extern "C" int fv_memcpy2d_async(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width,
+                                 int64_t height, int direction, void* stream) {
+  FV_REQUIRE(dst && src, "null pointer");
+  FV_REQUIRE(width >= 0 && height >= 0 && dpitch >= width && spitch >= width, "bad pitch / extent");
+  if (width == 0 || height == 0) return FV_OK;
+  FV_CUDA(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height,
+                            direction == 0 ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice,
+                            (cudaStream_t)stream));
+  return FV_OK;
+}

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "fv_version": (c_int, []),
     "fv_device_count": (c_int, [POINTER(c_int)]),
     "fv_launch_count": (c_int64, []),
+    "fv_memcpy2d_async": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "fv_kernel_params": (c_int, [c_double, c_double, c_int, POINTER(c_int), POINTER(c_double)]),
     "fv_next235even": (c_int64, [c_int64]),
     "fv_rotate_cut_scratch_bytes": (c_int64, [c_int64]),

@@ -36,7 +36,7 @@ from ..core import utils as core_utils
 from ..core.simulate import SimulationEngine, default_accuracy_dict
 from . import _lib
 from .beams import DeviceBeam, GPUBeamEvaluator, launch_weights
-from .nufft import ModeSet, NufftPlan
+from .nufft import ModeSet, NufftPlan, default_plan
 
 logger = logging.getLogger(__name__)
 
@@ -103,6 +103,17 @@ class SimulationPlan:
         return self.f_hi - self.f_lo
 
 
+_COPY_STREAMS: dict = {}
+
+
+def _copy_stream(dev) -> torch.cuda.Stream:
+    """One side stream per device for the result slabs' D2H copies."""
+    key = torch.device(dev).index
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
+
+
 def _next235even(n: int) -> int:
     return int(_lib.lib().fv_next235even(int(n)))
 
@@ -129,9 +140,10 @@ class GPUSimulationEngine(SimulationEngine):
         return torch.device("cuda", torch.cuda.current_device())
 
     def _nufft_plan(self, dev) -> NufftPlan:
-        if self._nufft is None or self._nufft.device != dev:
-            with torch.cuda.device(dev):
-                self._nufft = NufftPlan(dev)
+        """The process-wide plan of (device, current stream): its work areas and twiddle tables outlive
+        the engine, so that back-to-back ``simulate_vis`` calls do not pay a plan teardown + rebuild."""
+        with torch.cuda.device(dev):
+            self._nufft = default_plan()
         return self._nufft
 
     # ------------------------------------------------------------------------------------------
@@ -163,7 +175,13 @@ class GPUSimulationEngine(SimulationEngine):
             baselines = core_utils.get_pos_reds(ants, include_autos=True, representatives_only=True)
         baselines = [tuple(b) for b in baselines]
         nbls = len(baselines)
-        coherency, pol_sky = catalog.prepare_source_catalog(np.asarray(fluxes), polarized_beam=polarized)
+        fluxes = np.asarray(fluxes)
+        if fluxes.ndim == 2:
+            # Stokes I: the 0.5 I scaling and the cast (cpu/utils.py:52-53, cpu_simulate.py:622-626)
+            # are applied on the device after the upload of the caller's array as it is
+            coherency, pol_sky = None, False
+        else:
+            coherency, pol_sky = catalog.prepare_source_catalog(fluxes, polarized_beam=polarized)
         nsrc = int(np.size(dec))
 
         # ---- array geometry: gridded -> type 1; else plane rotation -> type 3 (:628-681)
@@ -213,12 +231,15 @@ class GPUSimulationEngine(SimulationEngine):
             eq_d = torch.as_tensor(eq).to(dev)
             # catalogue, frequency-major so that the gather through ascending src_idx coalesces
             # catalogue: uploaded as given, cast and transposed to frequency-major ON the device
-            coh_d = torch.as_tensor(np.ascontiguousarray(coherency)).to(dev).to(cdt)
             if pol_sky:
+                coh_d = torch.as_tensor(np.ascontiguousarray(coherency)).to(dev).to(cdt)
                 flux_d = coh_d.permute(1, 2, 3, 0).reshape(nfreqs, 4, nsrc).contiguous()
             else:
-                flux_d = coh_d.t().contiguous()
-            del coh_d
+                raw = torch.as_tensor(np.ascontiguousarray(fluxes)).to(dev)
+                half = raw * 0.5 if raw.is_complex() else raw.to(torch.float64) * 0.5
+                del raw
+                flux_d = half.to(cdt).t().contiguous()   # product in the caller's precision, then the cast
+                del half
             freqs_d = torch.as_tensor(freqs.astype(np.float64)).to(dev)
 
             order = int((beam_spline_opts or {}).get("order", 1))
@@ -344,9 +365,14 @@ class GPUSimulationEngine(SimulationEngine):
         return w
 
     def run_plan(self, plan: SimulationPlan, out: torch.Tensor | None = None,
-                 time_range=None) -> torch.Tensor:
+                 time_range=None, host_out: torch.Tensor | None = None) -> torch.Tensor:
         """Device-only hot loop (the GPU form of ``_evaluate_vis_chunk``, cpu_simulate.py:936-1069).
-        Returns the device tensor ``(nf_local, nt, P, nbls)`` in the final output layout."""
+        Returns the device tensor ``(nf_local, nt, P, nbls)`` in the final output layout.
+
+        ``host_out``: a page-locked host tensor of the same shape.  When given, every finished time
+        slab ``out[:, t]`` is copied into it on a second stream (``fv_memcpy2d_async``) while the next
+        time steps are computed -- the device form of the reference's ``vis[tc][..., fc] = future``
+        scatter (cpu_simulate.py:846-847); the caller synchronises the device before reading it."""
         dev, prec = plan.device, plan.precision
         L = _lib.lib()
         P = 4 if plan.polarized else 1
@@ -365,6 +391,8 @@ class GPUSimulationEngine(SimulationEngine):
             else:
                 out.zero_()
             if nfl == 0 or nt == 0 or plan.nbls == 0 or plan.nsrc == 0:
+                if host_out is not None:
+                    host_out.zero_()
                 return out
             w = self._workspace(plan)
             esz = out.element_size()
@@ -373,7 +401,17 @@ class GPUSimulationEngine(SimulationEngine):
             dim = 2 if (plan.use_type1 or plan.is_coplanar) else 3
             chunk = int(math.ceil(plan.nsrc / plan.nchunks))
             freqs64 = plan.freqs_host.astype(np.float64)
+            copy_st = None
+            if host_out is not None:
+                if tuple(host_out.shape) != tuple(out.shape) or host_out.dtype != out.dtype \
+                        or not host_out.is_contiguous() or not out.is_contiguous():
+                    raise ValueError("host_out must be a contiguous host tensor shaped and typed like the result")
+                copy_st = _copy_stream(dev)
+                copy_st.wait_stream(st)                      # the zero fill precedes every slab copy
+            slab = P * plan.nbls * esz
             for to, ti in enumerate(range(t_lo, t_hi)):
+                if to > 0 and copy_st is not None:
+                    self._stream_slab(out, host_out, to - 1, nfl, nt, slab, st, copy_st)
                 for ch in range(plan.nchunks):
                     lo, hi = ch * chunk, min(plan.nsrc, (ch + 1) * chunk)
                     if lo >= hi:
@@ -411,7 +449,19 @@ class GPUSimulationEngine(SimulationEngine):
                                 obase, sb_, sp_, pmap, pt.kmap.data_ptr() if pt.kmap is not None else 0,
                                 pt.conj.data_ptr() if pt.conj is not None else 0, accumulate=True)
                             self._nufft_batch(plan, w, nufft, pt, dim, xlim, scale, nb, epi)
+            if copy_st is not None:
+                self._stream_slab(out, host_out, nt - 1, nfl, nt, slab, st, copy_st)
+                st.wait_stream(copy_st)                      # `out` may be reused once the copies are done
             return out
+
+    @staticmethod
+    def _stream_slab(out, host_out, to, nfl, nt, slab, st, copy_st):
+        """Enqueue the D2H of time slab ``to`` (nf rows of ``slab`` bytes, ``nt * slab`` apart) behind
+        the work enqueued so far."""
+        copy_st.wait_stream(st)
+        _lib.check(_lib.lib().fv_memcpy2d_async(
+            host_out.data_ptr() + to * slab, nt * slab, out.data_ptr() + to * slab, nt * slab, slab, nfl,
+            0, copy_st.cuda_stream), "fv_memcpy2d_async")
 
     def _nufft_batch(self, plan, w, nufft, pt, dim, xlim, scale, nb, epi):
         W = w["W"][:nb]
@@ -474,9 +524,32 @@ class GPUSimulationEngine(SimulationEngine):
                             beam_spline_opts=beam_spline_opts, flat_array_tol=flat_array_tol,
                             coord_method_params=coord_method_params, force_use_type3=force_use_type3,
                             nchunks=nchunks, source_buffer=source_buffer, beam_coefs=beam_coefs)
-        out = self.run_plan(plan)
-        self.check_source_buffer(plan)
-        return self.finish(plan, out)
+        host = self._pinned_result(plan)
+        out = self.run_plan(plan, host_out=host)
+        if host is None:
+            self.check_source_buffer(plan)
+            return self.finish(plan, out)
+        self.check_source_buffer(plan)                       # reads the live counts back: synchronises
+        torch.cuda.current_stream(plan.device).synchronize()
+        return self._shape_result(plan, host.numpy())
+
+    @staticmethod
+    def _pinned_result(plan: SimulationPlan):
+        """Page-locked host block for the result (torch's caching host allocator reuses it across
+        calls); None when page-locking is refused (ulimit / memory pressure)."""
+        P = 4 if plan.polarized else 1
+        try:
+            return torch.empty((plan.nf_local, plan.ntimes, P, plan.nbls), dtype=_CDT[plan.precision],
+                               pin_memory=True)
+        except RuntimeError:
+            return None
+
+    @staticmethod
+    def _shape_result(plan: SimulationPlan, res: np.ndarray) -> np.ndarray:
+        nf, nt = res.shape[0], res.shape[1]
+        if plan.polarized:
+            return res.reshape(nf, nt, 2, 2, plan.nbls)
+        return res.reshape(nf, nt, plan.nbls)
 
     @staticmethod
     def finish(plan: SimulationPlan, out: torch.Tensor) -> np.ndarray:

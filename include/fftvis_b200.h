@@ -44,6 +44,13 @@ int fv_device_count(int* count_host);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 int64_t fv_launch_count(void);
 
+/* Strided host <-> device copy on `stream` (direction 0: device -> host, 1: host -> device; pitches and
+ * width in bytes).  Replaces the host scatter `vis[tc][..., fc] = future` (cpu_simulate.py:846-847):
+ * each finished time slab of the (nf, nt, P, nbls) result is streamed into the caller's page-locked
+ * array while later time steps are still being computed. */
+int fv_memcpy2d_async(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width,
+                      int64_t height, int direction, void* stream);
+
 /* ---- kernel / grid parameter rules (host only; finufft's published rules) */
 int fv_kernel_params(double eps, double upsampfac, int prec, int* w_host, double* beta_host);
 int64_t fv_next235even(int64_t n);
