@@ -152,8 +152,8 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
       cudaMemcpyAsync(hcyc, dbg_dev, 96, cudaMemcpyDeviceToHost, P->stream);
       cudaStreamSynchronize(P->stream);
       const double nw = 8.0 * (threads / 32);
-      fprintf(stderr, "[fv] t1 pass-1 cycles/warp: zero %.0f scan %.0f fill %.0f spread %.0f fft %.0f fftwait %.0f write %.0f hits/strip %.0f passA %.0f passB %.0f hits/warp %.1f passB-nonempty-frac %.3f passB-readL-cycles %.0f\n",
-              hcyc[0] / nw, hcyc[1] / nw, hcyc[2] / nw, hcyc[3] / nw, hcyc[4] / nw, hcyc[5] / nw, hcyc[6] / nw, hcyc[7] / nw, hcyc[8] / nw, hcyc[9] / nw, hcyc[10] / nw, (double)(hcyc[11] >> 32) / nw, (double)(hcyc[11] & 0xffffffffll) / nw);
+      fprintf(stderr, "[fv] t1 pass-1 cycles/warp: zero %.0f scan %.0f fill %.0f spread %.0f fft %.0f fftwait %.0f write %.0f\n",
+              hcyc[0] / nw, hcyc[1] / nw, hcyc[2] / nw, hcyc[3] / nw, hcyc[4] / nw, hcyc[5] / nw, hcyc[6] / nw);
     }
   }
   // ---- pass 2: FFT along y + deconvolve + gather -----------------------------------------------

@@ -40,6 +40,27 @@ template <typename C> __device__ __forceinline__ C c_add(C a, C b) { a.x += b.x;
 template <typename C> __device__ __forceinline__ C c_sub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
 template <typename C> __device__ __forceinline__ C c_muli(C a) { C r; r.x = -a.y; r.y = a.x; return r; }   // i * a
 
+// Shared-memory accesses by 32-bit shared address, as volatile PTX: the compiler keeps their relative
+// order (loads of the next hit's record stay ahead of the current hit's stores) and emits a single
+// LDS / STS each instead of re-deriving the shared window per access.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lds_i32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_u8(unsigned a) { int v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_real(unsigned a, float) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double lds_real(unsigned a, double) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds_cplx(unsigned a, float) {
+  float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v;
+}
+__device__ __forceinline__ double2 lds_cplx(unsigned a, double) {
+  double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts_cplx(unsigned a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts_cplx(unsigned a, double2 v) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+
 // r-point DFTs on registers, sign +1:  y_k = sum_q x_q exp(+2 pi i q k / r)
 template <typename T> __device__ __forceinline__ void dft2(cplx_t<T>* x) {
   const cplx_t<T> t = c_sub(x[0], x[1]);
@@ -319,9 +340,12 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   const T* zyp = a.zy + (int64_t)b * a.n_cap;
   const C* Wp = a.W + (int64_t)bpi * a.n_cap;
 
-  long long tph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  long long tc = clock64();
-#define T1_PHASE(i) do { if (a.dbg) { const long long t_ = clock64(); tph[i] += t_ - tc; tc = t_; } } while (0)
+  // optional per-phase cycle counters (development aid): lane 0 of every warp of the first strips adds
+  // its phase time straight to global memory, so that only the last time stamp stays live
+  long long tc = a.dbg ? clock64() : 0;
+  const bool dbg_me = a.dbg && lane == 0 && blockIdx.y == 0 && blockIdx.x < 8;
+#define T1_PHASE(i) do { if (a.dbg) { const long long t_ = clock64(); \
+    if (dbg_me) atomicAdd((unsigned long long*)&a.dbg[i], (unsigned long long)(t_ - tc)); tc = t_; } } while (0)
   {
     // clear the strip with 16-byte stores
     const int n16 = (int)(((size_t)NP * pstride * sizeof(C)) / 16);
@@ -331,7 +355,6 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   }
   for (int i = tid; i < a.st.tw_len; i += nthr) tw[i] = a.tw[i];
   for (int i = tid; i < a.ncols; i += nthr) colp[i] = a.col_pos[i];
-  if (tid < 2 * T1_MAXSEG) seg_cnt[tid] = 0;
   __syncthreads();
   T1_PHASE(0);
 
@@ -408,7 +431,6 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
     __syncthreads();
     T1_PHASE(1);
     const int next = shi;
-    tph[7] += nh;
     // ---- flush: evaluate kernels densely, then spread by row ownership -------------------------
     for (int c0 = 0; c0 < nh; c0 += T1_RC) {
       const int cn = min(T1_RC, nh - c0);
@@ -419,11 +441,6 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
           z0 = zxp[src];
           const int c0w = wrap_idx(ix0[src], nf);
           rec_i0x[h] = c0w;
-          if (use_seg) {
-            const int ks = c0w / seg;
-            const int key = 2 * ks + (c0w + w <= min(nf, (ks + 1) * seg) ? 0 : 1);
-            seg_list[key * T1_RC + atomicAdd(&seg_cnt[key], 1)] = (unsigned char)h;
-          }
 #pragma unroll
           for (int pp = 0; pp < NP; ++pp) rec_w[h * NP + pp] = Wp[(int64_t)pp * a.n_cap + src];
         } else {
@@ -441,67 +458,79 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
       __syncthreads();
       T1_PHASE(2);
       if (use_seg) {
-        // Spreading without atomics: warp = column segment.  A warp walks the hits whose columns lie
-        // wholly inside its segment, one hit at a time with the hit's w x w cells spread over its
-        // lanes.  The cells of one hit are distinct, different warps own different column ranges and a
-        // warp's hits are program-ordered: no races, and a deterministic sum order.  Hits that straddle
-        // a segment edge (or wrap) go in a second pass, each by the warp of the segment they start in.
-        for (int pass = 0; pass < 2; ++pass) {
-          const long long tp0 = clock64();
-          if (warp < nseg) {
-            // pass 0: hits wholly inside my segment; pass 1: hits that start in my segment and cross
-            // its upper edge (different edges are > w columns apart, so warps stay disjoint).  The
-            // list was filled with atomics; 32 entries at a time are taken in ascending hit order so
-            // that the sum order does not depend on the race.
-            const int key = 2 * warp + pass;
-            const int L = seg_cnt[key];
-            if (a.dbg && pass == 1) { tph[11] += (clock64() - tp0) + (L > 0 ? (1ll << 32) : 0); }
-            for (int lb = 0; lb < L; lb += 32) {
-              const int ln = min(32, L - lb);
-              const int e = lane < ln ? (int)seg_list[key * T1_RC + lb + lane] : INT_MAX;
-              int rank = 0;
-              for (int k = 0; k < ln; ++k) rank += __shfl_sync(0xffffffffu, e, k) < e ? 1 : 0;
-              for (int r = 0; r < ln; ++r) {
-                const int sl = __ffs(__ballot_sync(0xffffffffu, lane < ln && rank == r)) - 1;
-                const int h = __shfl_sync(0xffffffffu, e, sl);
-                // lane = (footprint row j, column group t): the hit's w x w cells are spread over
-                // w * G lanes, ceil(w / G) cells each; all cells of one hit are distinct
-                const int c0 = rec_i0x[h];
-                int rr = rec_d[h] + jrow;
-                if (rr >= nf) rr -= nf;
-                tph[10] += 1;
-                if (jrow < w && rr < rows) {
-                  const T ky = rec_ky[h * WMAX + jrow];
-                  const T* kx = rec_kx + h * WMAX;
-                  constexpr int CPL = WT > 0 ? (WT + (32 / WT) - 1) / (32 / WT) : kMaxW;   // cells per lane
-                  T kr[CPL];
-                  int cq[CPL];
-#pragma unroll
-                  for (int i = 0; i < CPL; ++i) {
-                    const int q = tcol + i * G;
-                    kr[i] = q < w ? kx[q] * ky : T(0);
-                    cq[i] = q < w ? (pass == 0 ? c0 + q : wrap_idx(c0 + q, nf)) : -1;
-                  }
-#pragma unroll
-                  for (int pp = 0; pp < NP; ++pp) {
-                    const C cw = rec_w[h * NP + pp];
-                    C* rowp = strip + pp * pstride + rr * pitch;
-                    C v[CPL];
-#pragma unroll
-                    for (int i = 0; i < CPL; ++i) if (cq[i] >= 0) v[i] = rowp[cq[i]];
-#pragma unroll
-                    for (int i = 0; i < CPL; ++i)
-                      if (cq[i] >= 0) { v[i].x += cw.x * kr[i]; v[i].y += cw.y * kr[i]; rowp[cq[i]] = v[i]; }
-                  }
-                }
-                __syncwarp();                              // the next hit may touch the same cells from other lanes
-              }
+        // Spreading without atomics: warp = column segment.  A warp walks, in ascending hit order, the
+        // hits whose footprint has columns in its segment (a hit that crosses a segment edge is taken by
+        // both neighbours, each adding only its own columns), one hit at a time with the hit's w x w
+        // cells spread over the lanes: lane = (footprint row, column group), ceil(w / G) cells each.
+        // The cells of one hit are distinct, warps own disjoint columns and a warp's hits are
+        // program-ordered: no races, a deterministic sum, and no CTA barrier inside the phase.
+        const int s0 = warp * seg, s1 = min(nf, s0 + seg);
+        if (warp < nseg && s0 < nf) {
+          unsigned char* sl = seg_list + warp * T1_RC;
+          // my hits, in order: ballot compaction over the chunk's first columns
+          int L = 0;
+          for (int hb = 0; hb < cn; hb += 32) {
+            const int hl = hb + lane;
+            bool mine = false;
+            if (hl < cn) {
+              const int c0 = rec_i0x[hl], c1 = c0 + w;       // columns [c0, c1), wrapped at nf
+              mine = (c0 < s1 && c1 > s0) || (c1 - nf > s0);
             }
-            __syncwarp();
-            if (lane == 0) seg_cnt[key] = 0;           // ready for the next chunk's fill
+            const unsigned ball = __ballot_sync(0xffffffffu, mine);
+            if (mine) sl[L + __popc(ball & ((1u << lane) - 1u))] = (unsigned char)hl;
+            L += __popc(ball);
           }
-          if (a.dbg) tph[8 + pass] += clock64() - tp0;
-          __syncthreads();
+          __syncwarp();
+          constexpr int CPL = WT > 0 ? (WT + (32 / WT) - 1) / (32 / WT) : kMaxW / 2;   // cells per lane (w <= 16: G >= 2)
+          const int jr = min(jrow, w - 1);
+          const bool lane_on = jrow < w;
+          const unsigned a_sl = smem_addr(sl), a_i0x = smem_addr(rec_i0x), a_d = smem_addr(rec_d);
+          const unsigned a_w = smem_addr(rec_w), a_strip = smem_addr(strip);
+          const unsigned a_ky = smem_addr(rec_ky) + jr * (unsigned)sizeof(T);
+          const unsigned a_kx = smem_addr(rec_kx) + tcol * (unsigned)sizeof(T);
+          const unsigned seglen = (unsigned)(s1 - s0);
+          // record of the next hit (its loads are issued before the current hit's stores)
+          int h = 0, c0 = 0, d = 0;
+          T ky = T(0), kx[CPL];
+          C cw = make_c<T>(T(0), T(0));
+          auto load_rec = [&](int r) {
+            h = lds_u8(a_sl + r);
+            c0 = lds_i32(a_i0x + 4u * h);
+            d = lds_i32(a_d + 4u * h);
+            cw = lds_cplx(a_w + (unsigned)(NP * sizeof(C)) * h, T(0));
+            ky = lds_real(a_ky + (unsigned)(WMAX * sizeof(T)) * h, T(0));
+#pragma unroll
+            for (int i = 0; i < CPL; ++i)
+              kx[i] = (tcol + i * G < w) ? lds_real(a_kx + (unsigned)(WMAX * sizeof(T)) * h + (unsigned)(i * G * sizeof(T)), T(0)) : T(0);
+          };
+          if (L > 0) load_rec(0);
+          for (int r = 0; r < L; ++r) {
+            // this hit's cells
+            int rr = d < rows ? d : d - nf;                  // first footprint row relative to the strip (may be < 0)
+            rr += jrow;
+            const bool row_ok = lane_on && (unsigned)rr < (unsigned)rows;
+            const unsigned a_row = a_strip + (unsigned)(rr * pitch) * (unsigned)sizeof(C);
+            unsigned ca[CPL];
+            bool ok[CPL];
+            T kr[CPL];
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+              int col = c0 + tcol + i * G;
+              if (col >= nf) col -= nf;
+              ok[i] = row_ok && (tcol + i * G < w) && (unsigned)(col - s0) < seglen;
+              ca[i] = a_row + (unsigned)col * (unsigned)sizeof(C);
+              kr[i] = kx[i] * ky;
+            }
+            const C cwc = cw;
+            C v[CPL];
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) if (ok[i]) v[i] = lds_cplx(ca[i], T(0));
+            if (r + 1 < L) load_rec(r + 1);
+#pragma unroll
+            for (int i = 0; i < CPL; ++i)
+              if (ok[i]) { v[i].x += cwc.x * kr[i]; v[i].y += cwc.y * kr[i]; sts_cplx(ca[i], v[i]); }
+            __syncwarp();                                  // the next hit may touch the same cells from other lanes
+          }
         }
       } else if (rb0 < rb1) {
         // several rows per warp (small grids held whole in one CTA): warp q owns strip rows
@@ -598,8 +627,6 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
     }
   }
   T1_PHASE(6);
-  if (a.dbg && lane == 0 && blockIdx.y == 0 && blockIdx.x < 8)
-    for (int i = 0; i < 12; ++i) atomicAdd((unsigned long long*)&a.dbg[i], (unsigned long long)tph[i]);
 #undef T1_PHASE
 }
 
