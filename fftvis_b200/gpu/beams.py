@@ -104,6 +104,36 @@ def launch_weights(prec, mode, beam_i: DeviceBeam, beam_j: DeviceBeam, az, za, s
         "fv_weights")
 
 
+def evaluate_beam_device(beam, az, za, polarized: bool, freq: float, prec: int = 2, order: int = 1) -> torch.Tensor:
+    """One ``fv_weights`` launch: the response of ``beam`` at host directions (az, za) for one
+    frequency, left on the device as ``(4, n)`` complex [vector component * 2 + feed] if
+    ``polarized`` else ``(1, n)`` complex (power in the real part)."""
+    _lib.require_gpu()
+    model = as_beam_model(beam)
+    if not polarized and model.beam_type != "power":
+        model = model.to_power() if hasattr(model, "to_power") else model
+    if isinstance(model, UVBeamTable) and model.Nfreqs > 1:
+        fi = int(np.argmin(np.abs(np.asarray(model.freq_array) - freq)))
+        model = UVBeamTable(model.data_array[:, :, fi:fi + 1], model.axis1_array,
+                            model.axis2_array, np.atleast_1d(model.freq_array[fi]), model.beam_type)
+    dbeam = DeviceBeam(model, prec, order)
+    n = int(np.size(az))
+    rdt, cdt = _RDT[prec], _CDT[prec]
+    az_d = torch.as_tensor(np.ascontiguousarray(az)).to("cuda", rdt)
+    za_d = torch.as_tensor(np.ascontiguousarray(za)).to("cuda", rdt)
+    idx = torch.arange(n, dtype=torch.int32, device="cuda")
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
+    freqs = torch.tensor([float(freq)], dtype=torch.float64, device="cuda")
+    P = 4 if polarized else 1
+    flux = torch.ones((1, n), dtype=cdt, device="cuda")
+    out = torch.empty((1, P, max(n, 1)), dtype=cdt, device="cuda")
+    ob = torch.empty((1, P, max(n, 1)), dtype=cdt, device="cuda")
+    if n:
+        launch_weights(prec, 1 if polarized else 0, dbeam, dbeam, az_d, za_d, idx, n_dev, n, freqs, 0, 1,
+                       flux, n, out, ob)
+    return ob[0, :, :n]
+
+
 class GPUBeamEvaluator(BeamEvaluator):
     """GPU implementation of the beam evaluator."""
 
@@ -117,32 +147,11 @@ class GPUBeamEvaluator(BeamEvaluator):
         self.polarized = polarized
         self.freq = freq
         self.spline_opts = spline_opts or {}
-        model = as_beam_model(beam)
-        if not polarized and model.beam_type != "power":
-            model = model.to_power() if hasattr(model, "to_power") else model
         az = np.asarray(az)
         prec = 1 if az.dtype == np.float32 else 2
-        order = int(self.spline_opts.get("order", 1))
-        if isinstance(model, UVBeamTable) and model.Nfreqs > 1:
-            fi = int(np.argmin(np.abs(np.asarray(model.freq_array) - freq)))
-            model = UVBeamTable(model.data_array[:, :, fi:fi + 1], model.axis1_array,
-                                model.axis2_array, np.atleast_1d(model.freq_array[fi]), model.beam_type)
-        dbeam = DeviceBeam(model, prec, order)
         n = az.size
-        rdt, cdt = _RDT[prec], _CDT[prec]
-        az_d = torch.as_tensor(np.ascontiguousarray(az)).to("cuda", rdt)
-        za_d = torch.as_tensor(np.ascontiguousarray(za)).to("cuda", rdt)
-        idx = torch.arange(n, dtype=torch.int32, device="cuda")
-        n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
-        freqs = torch.tensor([float(freq)], dtype=torch.float64, device="cuda")
-        P = 4 if polarized else 1
-        flux = torch.ones((1, n), dtype=cdt, device="cuda")
-        out = torch.empty((1, P, max(n, 1)), dtype=cdt, device="cuda")
-        ob = torch.empty((1, P, max(n, 1)), dtype=cdt, device="cuda")
-        if n:
-            launch_weights(prec, 1 if polarized else 0, dbeam, dbeam, az_d, za_d, idx, n_dev, n, freqs, 0, 1,
-                           flux, n, out, ob)
-        res = ob[0, :, :n].cpu().numpy()
+        ob = evaluate_beam_device(beam, az, za, polarized, freq, prec, int(self.spline_opts.get("order", 1)))
+        res = ob.cpu().numpy()
         interp_beam = res.reshape(2, 2, n) if polarized else res[0].real.astype(az.dtype)
         if check:
             sm = np.sum(interp_beam)
