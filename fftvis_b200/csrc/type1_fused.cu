@@ -91,7 +91,9 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
 
   // ---- pass 1: spread + FFT along x ------------------------------------------------------------
   const int wmax = (w == 7 || w == 9 || w == 11 || w == 13 || w == 14) ? w : kMaxW;
-  const size_t row_bytes = sizeof(C) * pitch;
+  const int bank_mod = 128 / (int)sizeof(C);                 // elements per shared-memory bank sweep
+  const size_t row_bytes = sizeof(C) * (nf + bank_mod);      // pass 1: upper bound of the padded row (pitch1 below)
+  const size_t row_bytes2 = sizeof(C) * pitch;               // pass 2 column pitch
   const size_t smem_max = 227 * 1024 - 1024;
   // strip height R and CTA size: whole grid in one CTA when it fits; otherwise 16 rows x 512 threads
   // (one row per warp) if that fits, else 8 rows x 256 threads
@@ -109,6 +111,19 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
     if (R > 8) R -= R % 8;
   }
   int threads = thr_for(R);
+  // Row pitch of the pass-1 strip: the spreader's lanes are (footprint row, column group) pairs that touch
+  // cell (row * pitch + column group); with pitch = G (segment path) or w (row-block path) modulo one bank
+  // sweep, the 32 lanes of one instruction fall in 32 / 16 distinct banks -- no conflicts (pitch = nf + 1
+  // measured 3-4 wavefronts per access in the spreader).
+  int pitch1;
+  {
+    const int nwarps = threads / 32, G = std::max(1, 32 / w);
+    const int nseg = std::min(std::min(nwarps, T1_MAXSEG), (int)(nf / (4 * w)));
+    const bool use_seg = nseg >= std::min(nwarps, 8);
+    const int want = (use_seg ? G : w) % bank_mod;
+    pitch1 = (int)nf + 1;
+    while (pitch1 % bank_mod != want) ++pitch1;
+  }
   size_t fixed1 = t1_spread_fixed_smem<T>((int)nf, wmax, threads, np);
   while (R > 1 && fixed1 + np * row_bytes * R > smem_max) --R;
   if (fixed1 + np * row_bytes * R > smem_max) { set_error("fine-grid row does not fit shared memory: use the cuFFT type-1 path"); return FV_ERR_UNSUPPORTED; }
@@ -128,14 +143,14 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   }
   T1SpreadArgs<T> a{};
   a.n_dev = n_dev; a.n_cap = n_cap; a.ix0 = ix0; a.iy0 = iy0; a.zx = zx; a.zy = zy;
-  a.nf = (int)nf; a.R = R; a.pitch = pitch; a.w = w;
+  a.nf = (int)nf; a.R = R; a.pitch = pitch1; a.w = w;
   a.beta = (T)beta; a.c = (T)(4.0 / ((double)w * w)); a.halfw = (T)(w / 2.0);
   a.ntr = ntr; a.W = (const C*)W; a.tw = (const C*)F->tw; a.st = F->st;
   a.ncols = ncols; a.col_pos = tab->col_pos; a.Tbuf = (C*)P->tbuf;
   {
     StageScope ts(P, FV_STAGE_SPREAD);
     dim3 grid(ceil_div(nf, R), np == 4 ? nb : nb * ntr);
-    const size_t smem = fixed1 + np * row_bytes * R;
+    const size_t smem = fixed1 + np * sizeof(C) * pitch1 * R;
     static const bool dbg = getenv("FV_DEBUG") != nullptr;
     static long long* dbg_dev = nullptr;
     if (dbg) {
@@ -158,11 +173,11 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   }
   // ---- pass 2: FFT along y + deconvolve + gather -----------------------------------------------
   const size_t fixed2 = sizeof(C) * nf;
-  int cpc = P->t1_cols > 0 ? P->t1_cols : (int)std::max<size_t>(1, (100 * 1024 - std::min<size_t>(fixed2, 99 * 1024)) / row_bytes);
+  int cpc = P->t1_cols > 0 ? P->t1_cols : (int)std::max<size_t>(1, (100 * 1024 - std::min<size_t>(fixed2, 99 * 1024)) / row_bytes2);
   cpc = std::min(cpc, 16);
   if (cpc >= 8) cpc -= cpc % 8;
   cpc = std::min(cpc, ncols);
-  while (cpc > 1 && fixed2 + row_bytes * cpc > smem_max) --cpc;
+  while (cpc > 1 && fixed2 + row_bytes2 * cpc > smem_max) --cpc;
   T1GatherArgs<T> g{};
   g.Tbuf = (const C*)P->tbuf; g.nf = (int)nf; g.pitch = pitch; g.ncols = ncols; g.cols_per_cta = cpc; g.ntr = ntr;
   g.tw = (const C*)F->tw; g.st = F->st; g.col_off = tab->col_off; g.s_k = tab->s_k; g.s_pos = tab->s_pos;
@@ -170,7 +185,7 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   {
     StageScope ts(P, FV_STAGE_GATHER);
     auto kern = t1_ffty_gather_kernel<T>;
-    const size_t smem = fixed2 + row_bytes * cpc;
+    const size_t smem = fixed2 + row_bytes2 * cpc;
     FV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(ncols, cpc), nb * ntr);
     const int gthreads = std::min(T1_THREADS, std::max(64, 32 * cpc));     // one warp per column
