@@ -652,6 +652,7 @@ static int get_smem_fft(fv_plan* P, int prec, int64_t nf, fv_plan::SmemFft** out
     f.st.radix[i] = rad[i];
     const int64_t m = cur / rad[i];
     f.st.inv_m[i] = m == 1 ? 0u : (unsigned)(((1ull << 32) / (unsigned long long)m) + 1ull);
+    f.st.hw[i] = (m >= 9 && m <= 15 && (m & 1)) ? (int)m : 16;
     cur = m;
   }
   // digit-reversed output positions

@@ -34,6 +34,8 @@ struct FftStages {
   int tw_off[T1_MAX_STAGES];       // start of the stage's twiddles in the table: entry (q - 1) * m + j holds
                                    // exp(+2 pi i j q / n): consecutive lanes (j) read consecutive words
   int tw_len;                      // total table length (<= N)
+  int hw[T1_MAX_STAGES];           // butterflies per half-warp of the wide-radix stages: 16, or m when 9 <= m <= 15
+                                   // is odd (a half-warp then stays inside one block: no bank conflicts)
 };
 
 template <typename C> __device__ __forceinline__ C c_add(C a, C b) { a.x += b.x; a.y += b.y; return a; }
@@ -151,15 +153,19 @@ __device__ __forceinline__ void dft_r(cplx_t<T>* x) {
 // every load issued before the first store (the butterflies are disjoint, which the compiler cannot
 // prove for shared memory): the second butterfly's loads overlap the first one's arithmetic.
 template <typename T, int R>
-__device__ __forceinline__ void fft_stage(cplx_t<T>* data, int nvec, int pitch, int N, int n, unsigned inv,
+__device__ __forceinline__ void fft_stage(cplx_t<T>* data, int nvec, int pitch, int N, int n, unsigned inv, int hw,
                                           const cplx_t<T>* __restrict__ tws, int lane, int warp, int nwarps) {
   using C = cplx_t<T>;
   const int m = n / R, per_vec = N / R;
   for (int v = warp; v < nvec; v += nwarps) {
     C* vec = data + v * pitch;
     if (R >= 8) {
-      // wide butterfly: one per iteration (register budget), loads before stores
-      for (int t = lane; t < per_vec; t += 32) {
+      // wide butterfly: one per iteration (register budget), loads before stores.  Lanes take
+      // butterflies half-warp by half-warp, `hw` each (16, or the sub-length m when that keeps the 16
+      // lanes of a shared-memory wavefront inside one block of the stage).
+      for (int t0 = (lane >> 4) * hw; t0 < per_vec; t0 += 2 * hw) {
+        const int t = t0 + (lane & 15);
+        if ((lane & 15) >= hw || t >= per_vec) continue;
         const int blk = inv ? (int)__umulhi((unsigned)t, inv) : t;
         const int j = t - blk * m;
         const int base = blk * n + j;
@@ -220,14 +226,15 @@ __device__ void smem_fft(cplx_t<T>* data, int nvec, int pitch, int N, const cplx
   for (int s = 0; s < st.nstage; ++s) {
     const int r = st.radix[s];
     const unsigned inv = st.inv_m[s];            // 0 when m == 1
+    const int hw = st.hw[s];
     const cplx_t<T>* tws = tw + st.tw_off[s];
     switch (r) {
-      case 15: fft_stage<T, 15>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
-      case 8: fft_stage<T, 8>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
-      case 4: fft_stage<T, 4>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
-      case 2: fft_stage<T, 2>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
-      case 5: fft_stage<T, 5>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
-      default: fft_stage<T, 3>(data, nvec, pitch, N, n, inv, tws, lane, warp, nwarps); break;
+      case 15: fft_stage<T, 15>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
+      case 8: fft_stage<T, 8>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
+      case 4: fft_stage<T, 4>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
+      case 2: fft_stage<T, 2>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
+      case 5: fft_stage<T, 5>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
+      default: fft_stage<T, 3>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
     }
     __syncwarp();                                // a vector's stages only depend on that vector (one warp)
     n /= r;
@@ -346,15 +353,28 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   const bool dbg_me = a.dbg && lane == 0 && blockIdx.y == 0 && blockIdx.x < 8;
 #define T1_PHASE(i) do { if (a.dbg) { const long long t_ = clock64(); \
     if (dbg_me) atomicAdd((unsigned long long*)&a.dbg[i], (unsigned long long)(t_ - tc)); tc = t_; } } while (0)
+  // the prologue's global loads (twiddles, needed-column positions) are issued before the strip is
+  // cleared, so that their latency hides under the clear
+  C tw_pre[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) { const int i = tid + u * nthr; if (i < a.st.tw_len) tw_pre[u] = a.tw[i]; }
+  const int cp_pre = tid < a.ncols ? a.col_pos[tid] : 0;
   {
-    // clear the strip with 16-byte stores
+    // clear the strip with 16-byte stores (32-bit shared addresses: one STS.128 + one add per store)
     const int n16 = (int)(((size_t)NP * pstride * sizeof(C)) / 16);
-    int4* z4 = reinterpret_cast<int4*>(strip);
-    for (int i = tid; i < n16; i += nthr) z4[i] = make_int4(0, 0, 0, 0);
+    const unsigned a0 = smem_addr(strip);
+    const unsigned step = 16u * (unsigned)nthr;
+    unsigned ap = a0 + 16u * (unsigned)tid;
+    const unsigned aend = a0 + 16u * (unsigned)n16;
+#pragma unroll 4
+    for (; ap < aend; ap += step) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" :: "r"(ap), "r"(0) : "memory");
     for (int i = n16 * (16 / (int)sizeof(C)) + tid; i < NP * pstride; i += nthr) strip[i] = make_c<T>(T(0), T(0));
   }
-  for (int i = tid; i < a.st.tw_len; i += nthr) tw[i] = a.tw[i];
-  for (int i = tid; i < a.ncols; i += nthr) colp[i] = a.col_pos[i];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) { const int i = tid + u * nthr; if (i < a.st.tw_len) tw[i] = tw_pre[u]; }
+  for (int i = tid + 2 * nthr; i < a.st.tw_len; i += nthr) tw[i] = a.tw[i];
+  if (tid < a.ncols) colp[tid] = cp_pre;
+  for (int i = tid + nthr; i < a.ncols; i += nthr) colp[i] = a.col_pos[i];
   __syncthreads();
   T1_PHASE(0);
 
@@ -614,16 +634,31 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
 
   // needed columns of this strip -> T[col][row] (rows contiguous)
   const int total = a.ncols * rows;
-  const unsigned inv_rows = rows > 1 ? (unsigned)(((1ull << 32) / (unsigned)rows) + 1ull) : 0u;
+  const unsigned inv_rows = rows > 1 ? 0xFFFFFFFFu / (unsigned)rows + 1u : 0u;   // floor(2^32 / rows) + 1 without a 64-bit division
 #pragma unroll
   for (int pp = 0; pp < NP; ++pp) {
     C* Tb = a.Tbuf + (int64_t)(bpi + pp) * a.ncols * nf + r0;
     const C* sp = strip + pp * pstride;
+    if (sizeof(C) == 8 && ((rows | r0) & 1) == 0) {
+      // two consecutive rows per thread: 16-byte stores (the store-instruction rate bounds this phase)
+      const int np2 = rows >> 1, total2 = a.ncols * np2;
+      const unsigned inv_np2 = np2 > 1 ? 0xFFFFFFFFu / (unsigned)np2 + 1u : 0u;
+      const unsigned a_sp = smem_addr(sp);
+#pragma unroll 2
+      for (int i = tid; i < total2; i += nthr) {
+        const int ci = inv_np2 ? (int)__umulhi((unsigned)i, inv_np2) : i;
+        const int pr = i - ci * np2;
+        const unsigned ac = a_sp + (unsigned)(2 * pr * pitch + (int)colp[ci]) * 8u;
+        const float2 v0 = lds_cplx(ac, 0.f), v1 = lds_cplx(ac + (unsigned)pitch * 8u, 0.f);
+        *reinterpret_cast<float4*>(reinterpret_cast<float2*>(Tb) + (int64_t)ci * nf + 2 * pr) = make_float4(v0.x, v0.y, v1.x, v1.y);
+      }
+    } else {
 #pragma unroll 4
-    for (int i = tid; i < total; i += nthr) {
-      const int ci = inv_rows ? (int)__umulhi((unsigned)i, inv_rows) : i;
-      const int rr = i - ci * rows;
-      Tb[(int64_t)ci * nf + rr] = sp[rr * pitch + colp[ci]];
+      for (int i = tid; i < total; i += nthr) {
+        const int ci = inv_rows ? (int)__umulhi((unsigned)i, inv_rows) : i;
+        const int rr = i - ci * rows;
+        Tb[(int64_t)ci * nf + rr] = sp[rr * pitch + colp[ci]];
+      }
     }
   }
   T1_PHASE(6);
