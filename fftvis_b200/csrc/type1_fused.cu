@@ -115,10 +115,10 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   // cell (row * pitch + column group); with pitch = G (segment path) or w (row-block path) modulo one bank
   // sweep, the 32 lanes of one instruction fall in 32 / 16 distinct banks -- no conflicts (pitch = nf + 1
   // measured 3-4 wavefronts per access in the spreader).
-  int pitch1;
+  int pitch1, nseg;
   {
     const int nwarps = threads / 32, G = std::max(1, 32 / w);
-    const int nseg = std::min(std::min(nwarps, T1_MAXSEG), (int)(nf / (4 * w)));
+    nseg = std::min(std::min(nwarps, T1_MAXSEG), (int)(nf / (4 * w)));
     const bool use_seg = nseg >= std::min(nwarps, 8);
     const int want = (use_seg ? G : w) % bank_mod;
     pitch1 = (int)nf + 1;
@@ -144,6 +144,8 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   T1SpreadArgs<T> a{};
   a.n_dev = n_dev; a.n_cap = n_cap; a.ix0 = ix0; a.iy0 = iy0; a.zx = zx; a.zy = zy;
   a.nf = (int)nf; a.R = R; a.pitch = pitch1; a.w = w;
+  a.nseg = nseg; a.seg = nseg > 0 ? (int)((nf + nseg - 1) / nseg) : (int)nf;
+  a.inv_ntr = ntr > 1 ? 0xFFFFFFFFu / (unsigned)ntr + 1u : 0u;
   a.beta = (T)beta; a.c = (T)(4.0 / ((double)w * w)); a.halfw = (T)(w / 2.0);
   a.ntr = ntr; a.W = (const C*)W; a.tw = (const C*)F->tw; a.st = F->st;
   a.ncols = ncols; a.col_pos = tab->col_pos; a.Tbuf = (C*)P->tbuf;

@@ -228,16 +228,15 @@ __device__ void smem_fft(cplx_t<T>* data, int nvec, int pitch, int N, const cplx
     const unsigned inv = st.inv_m[s];            // 0 when m == 1
     const int hw = st.hw[s];
     const cplx_t<T>* tws = tw + st.tw_off[s];
-    switch (r) {
-      case 15: fft_stage<T, 15>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
-      case 8: fft_stage<T, 8>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
-      case 4: fft_stage<T, 4>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
-      case 2: fft_stage<T, 2>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
-      case 5: fft_stage<T, 5>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
-      default: fft_stage<T, 3>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); break;
+    switch (r) {                                 // the next sub-length by a constant division in every case
+      case 15: fft_stage<T, 15>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); n /= 15; break;
+      case 8: fft_stage<T, 8>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); n /= 8; break;
+      case 4: fft_stage<T, 4>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); n /= 4; break;
+      case 2: fft_stage<T, 2>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); n /= 2; break;
+      case 5: fft_stage<T, 5>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); n /= 5; break;
+      default: fft_stage<T, 3>(data, nvec, pitch, N, n, inv, hw, tws, lane, warp, nwarps); n /= 3; break;
     }
     __syncwarp();                                // a vector's stages only depend on that vector (one warp)
-    n /= r;
   }
 }
 
@@ -246,8 +245,10 @@ struct T1SpreadArgs {
   const int32_t* n_dev;
   int64_t n_cap;
   int nf, R, pitch, w;
+  int nseg, seg;                 // column segments of the segment spreader (host: min(warps, T1_MAXSEG, nf / 4w))
   T beta, c, halfw;
   int ntr;
+  unsigned inv_ntr;              // floor(2^32 / ntr) + 1 (0 when ntr == 1)
   const cplx_t<T>* W;            // (nb, ntr, n_cap)
   // per (frequency, source) fold results from t1_prep_kernel, each (nb, n_cap)
   const int32_t* ix0; const int32_t* iy0;   // first grid column / row of the footprint (may be < 0)
@@ -327,17 +328,14 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
 
   const int nf = a.nf, pitch = a.pitch;
   const int bpi = NP == 1 ? blockIdx.y : blockIdx.y * a.ntr;   // index of the (first) product's transform
-  const int b = NP == 1 ? blockIdx.y / a.ntr : blockIdx.y;
+  const int b = NP == 1 ? (a.inv_ntr ? (int)__umulhi(blockIdx.y, a.inv_ntr) : (int)blockIdx.y) : (int)blockIdx.y;
   const int r0 = blockIdx.x * a.R;
   const int rows = min(a.R, nf - r0);
   const int n = *a.n_dev;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-  const int rpw = (rows + nwarps - 1) / nwarps;            // strip rows owned by each warp
-  const int rb0 = warp * rpw, rb1 = min(rows, rb0 + rpw);
   const int G = 32 / w;                                    // footprint rows per warp instruction (multi-row path)
   // column segments of the thread-per-row path: at least 4 w columns each, one warp per segment
-  const int nseg = min(min(nwarps, T1_MAXSEG), nf / (4 * w));
-  const int seg = nseg > 0 ? (nf + nseg - 1) / nseg : nf;
+  const int nseg = a.nseg, seg = a.seg;
   const bool use_seg = nseg >= min(nwarps, 8);             // narrow grids: row-block ownership instead
   const int jj = lane / w, jx = lane - jj * w;              // multi-row path: (row in group, column)
   const int jrow = lane / G, tcol = lane - jrow * G;       // segment path: (footprint row, column group)
@@ -552,7 +550,9 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
             __syncwarp();                                  // the next hit may touch the same cells from other lanes
           }
         }
-      } else if (rb0 < rb1) {
+      } else if (warp * ((rows + nwarps - 1) / nwarps) < rows) {
+        const int rpw = (rows + nwarps - 1) / nwarps;        // strip rows owned by each warp
+        const int rb0 = warp * rpw, rb1 = min(rows, rb0 + rpw);
         // several rows per warp (small grids held whole in one CTA): warp q owns strip rows
         // [q rpw, (q + 1) rpw); one hit at a time, G of its footprint rows per instruction (lane =
         // row in group * w + column).  Lanes of one instruction touch distinct cells and no other
