@@ -175,7 +175,8 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   }
   // ---- pass 2: FFT along y + deconvolve + gather -----------------------------------------------
   const size_t fixed2 = sizeof(C) * nf;
-  int cpc = P->t1_cols > 0 ? P->t1_cols : (int)std::max<size_t>(1, (100 * 1024 - std::min<size_t>(fixed2, 99 * 1024)) / row_bytes2);
+  const size_t gbudget = (t1_limits<T>::gather_blocks >= 3 ? 74 : 100) * 1024;   // shared memory per CTA: 3 or 2 CTAs per SM
+  int cpc = P->t1_cols > 0 ? P->t1_cols : (int)std::max<size_t>(1, (gbudget - std::min<size_t>(fixed2, gbudget - 1024)) / row_bytes2);
   cpc = std::min(cpc, 16);
   if (cpc >= 8) cpc -= cpc % 8;
   cpc = std::min(cpc, ncols);

@@ -298,7 +298,7 @@ inline size_t t1_spread_fixed_smem(int nf, int wmax, int threads, int np = 1) {
 }
 
 template <typename T> struct t1_limits;
-template <> struct t1_limits<float> { static constexpr int spread_threads = 768, gather_blocks = 2; };
+template <> struct t1_limits<float> { static constexpr int spread_threads = 768, gather_blocks = 3; };
 template <> struct t1_limits<double> { static constexpr int spread_threads = 512, gather_blocks = 1; };
 
 // NP = products spread by one CTA: 1 (grid.y = frequencies x products) or 4 (grid.y = frequencies; the
