@@ -356,13 +356,16 @@ def run_gpu(args):
             ach = alg / (sp_ms / sp_n * 1e-3) / 1e9
             kname = ("t1_spread_fftx_kernel (fused spread + FFT-x, grid in shared memory)"
                      if eng.type1_method == "fused" else "spread_kernel (type 1, global grid)")
-            traffic = None
+            traffic, on_chip = None, None
             tf = ROOT / "profiles" / "r01_traffic.json"
             if tf.exists() and eng.type1_method == "fused" and w["name"] == "cfg2" and plan2.freq_batch == 37:
-                traffic = json.loads(tf.read_text()).get("cfg2", {}).get("t1_spread_fftx_kernel")
+                prof = json.loads(tf.read_text())
+                traffic = prof.get("cfg2", {}).get("t1_spread_fftx_kernel")
+                on_chip = prof.get("cfg2_ncu")        # ncu: issue-active and shared-memory pipe utilisation
             roof = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                     "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                    "alg_bytes_per_launch": alg, "avg_launch_ms": sp_ms / sp_n, "launches": sp_n}
+                    "alg_bytes_per_launch": alg, "avg_launch_ms": sp_ms / sp_n, "launches": sp_n,
+                    "on_chip_ncu": on_chip}
         stage_share = {k: {"ms": v[0], "launches": v[1], "share_of_step": v[0] / ms if ms else None}
                        for k, v in stages.items()}
         cpu_val, cpu_desc, cores, _ = cpu_sample(w, nbls, budget_s=args.cpu_budget)

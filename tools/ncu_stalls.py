@@ -18,7 +18,7 @@ marks = [("fft butterflies + stages", 1), ("kernel prologue + strip clear", line
          ("source scan", line_of("which sources' w-row footprints touch this strip")),
          ("records + kernel samples (fill)", line_of("flush: evaluate kernels densely")),
          ("spread (column segments)", line_of("if (use_seg) {")),
-         ("spread (row blocks, small grids)", line_of("} else if (rb0 < rb1) {")),
+         ("spread (row blocks, small grids)", line_of("} else if (warp * ((rows + nwarps - 1) / nwarps) < rows) {")),
          ("row FFT call + write-out", line_of("rows of all products are `pitch` apart"))]
 def phase(loc):
     if loc is None:
