@@ -67,19 +67,24 @@ class DeviceBeam:
                 else:
                     coef[k] = ndimage.spline_filter(flat[k], order=3, output=np.float64, mode="nearest")
             data = coef.reshape(padded.shape)
+        # upload the table as it is and re-lay it out on the device (a host transpose of a 1024-frequency
+        # E-field table is a multi-GB strided copy)
+        dev_data = torch.as_tensor(data).to(device)
         if self.is_power:
-            host = np.ascontiguousarray(np.real(data[0, 0]))                      # (nf, nza, naz)
             dt = _RDT[precision]
+            tab = dev_data[0, 0]                                                   # (nf, nza, naz)
+            tab = tab.real if tab.is_complex() else tab
         else:
-            nf = data.shape[2]
-            host = np.ascontiguousarray(
-                np.transpose(data, (2, 0, 1, 3, 4)).reshape(nf, 4, data.shape[3], data.shape[4]))
             dt = _CDT[precision]
-        self.table = torch.as_tensor(host).to(device=device, dtype=dt).contiguous()
-        self.nfreq_table = host.shape[0]
+            nf = data.shape[2]
+            tab = dev_data.permute(2, 0, 1, 3, 4).reshape(nf, 4, data.shape[3], data.shape[4])
+        self.table = tab.to(dtype=dt).contiguous()
+        del dev_data, tab
+        host_shape = tuple(self.table.shape)
+        self.nfreq_table = host_shape[0]
         d = self.desc
         d.table = self.table.data_ptr()
-        d.nza, d.naz = int(host.shape[-2]), int(host.shape[-1])
+        d.nza, d.naz = int(host_shape[-2]), int(host_shape[-1])
         d.az_wrap_period = int(az.size) if periodic else 0
         d.az_pad = pad
         d.spline_pad = spad
