@@ -129,20 +129,26 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   if (fixed1 + np * row_bytes * R > smem_max) { set_error("fine-grid row does not fit shared memory: use the cuFFT type-1 path"); return FV_ERR_UNSUPPORTED; }
   // fold every (frequency, source) point once
   const size_t per = (size_t)nb * n_cap;
-  rc = ensure(&P->prep, &P->prep_bytes, per * (2 * sizeof(int32_t) + 2 * sizeof(T)));
+  const int nstrips = ceil_div(nf, R);
+  const bool masks = nstrips > 1 && nstrips <= 64;           // strip membership of every source as two 32-bit masks
+  rc = ensure(&P->prep, &P->prep_bytes, per * (4 * sizeof(int32_t) + 2 * sizeof(T)));
   if (rc) return rc;
   int32_t* ix0 = (int32_t*)P->prep;
   int32_t* iy0 = ix0 + per;
-  T* zx = (T*)(iy0 + per);
+  uint32_t* hm0 = (uint32_t*)(iy0 + per);
+  uint32_t* hm1 = hm0 + per;
+  T* zx = (T*)(hm1 + per);
   T* zy = zx + per;
   {
     StageScope ts(P, FV_STAGE_ZERO);
     dim3 grid(ceil_div(n_cap, 256), nb);
-    t1_prep_kernel<T><<<grid, 256, 0, P->stream>>>((const T*)bx, (const T*)by, n_dev, n_cap, P->bp_dev, (int)nf, w, ix0, iy0, zx, zy);
+    t1_prep_kernel<T><<<grid, 256, 0, P->stream>>>((const T*)bx, (const T*)by, n_dev, n_cap, P->bp_dev, (int)nf, w, ix0, iy0, zx, zy,
+                                                   R, nstrips, masks ? hm0 : nullptr, masks ? hm1 : nullptr);
     FV_LAUNCH_CHECK();
   }
   T1SpreadArgs<T> a{};
   a.n_dev = n_dev; a.n_cap = n_cap; a.ix0 = ix0; a.iy0 = iy0; a.zx = zx; a.zy = zy;
+  a.hm0 = masks ? hm0 : nullptr; a.hm1 = masks ? hm1 : nullptr;
   a.nf = (int)nf; a.R = R; a.pitch = pitch1; a.w = w;
   a.nseg = nseg; a.seg = nseg > 0 ? (int)((nf + nseg - 1) / nseg) : (int)nf;
   a.inv_ntr = ntr > 1 ? 0xFFFFFFFFu / (unsigned)ntr + 1u : 0u;

@@ -253,6 +253,7 @@ struct T1SpreadArgs {
   // per (frequency, source) fold results from t1_prep_kernel, each (nb, n_cap)
   const int32_t* ix0; const int32_t* iy0;   // first grid column / row of the footprint (may be < 0)
   const T* zx; const T* zy;                 // kernel argument of that first cell
+  const uint32_t* hm0; const uint32_t* hm1; // strip masks of every (frequency, source) (null: more than 64 strips)
   const cplx_t<T>* tw;           // per-stage twiddle tables (FftStages::tw_off), <= nf entries
   FftStages st;
   int ncols;
@@ -268,7 +269,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 t1_prep_kernel(const T* __restrict__ bx, const T* __restrict__ by, const int32_t* __restrict__ n_dev,
                int64_t n_cap, const BatchParams* __restrict__ bp, int nf, int w, int32_t* __restrict__ ix0,
-               int32_t* __restrict__ iy0, T* __restrict__ zx, T* __restrict__ zy) {
+               int32_t* __restrict__ iy0, T* __restrict__ zx, T* __restrict__ zy, int R, int nstrips,
+               uint32_t* __restrict__ hm0, uint32_t* __restrict__ hm1) {
   const int n = *n_dev;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
@@ -280,6 +282,20 @@ t1_prep_kernel(const T* __restrict__ bx, const T* __restrict__ by, const int32_t
   const double gy = fold_grid((double)(by[s] * smul), nf), giy = ceil(gy - hw);
   ix0[o] = (int)gix; zx[o] = (T)(gix - gx);
   iy0[o] = (int)giy; zy[o] = (T)(giy - gy);
+  if (hm0) {
+    // which strips (of R rows; at most 64) the w footprint rows touch, as two 32-bit masks: the strip
+    // CTAs of pass 1 then test one bit per source instead of redoing the row arithmetic
+    const int y = (int)giy < 0 ? (int)giy + nf : (int)giy;
+    const int first = y / R, last_row = y + w - 1;
+    unsigned long long m = 0ull;
+    if (last_row < nf) {
+      for (int st = first, e = last_row / R; st <= e; ++st) m |= 1ull << st;
+    } else {
+      for (int st = first; st < nstrips; ++st) m |= 1ull << st;
+      for (int st = 0, e = (last_row - nf) / R; st <= e; ++st) m |= 1ull << st;
+    }
+    hm0[o] = (uint32_t)m; hm1[o] = (uint32_t)(m >> 32);
+  }
 }
 
 constexpr int T1_RC = 192;        // hit records evaluated and spread per flush chunk
@@ -380,8 +396,13 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
   // Two passes over a range of sources: count per warp, then store at deterministic offsets (warp-major
   // order); one barrier each instead of two per tile.  The range is everything left (up to the 16-bit
   // offset limit) when its hits fit the list, else the worst-case-safe `lcap` sources.
-  auto is_hit = [&](int yrow) {
-    int d = yrow - r0;
+  const bool masked = a.hm0 != nullptr;
+  const int32_t* scan_src = masked ? reinterpret_cast<const int32_t*>((blockIdx.x < 32 ? a.hm0 : a.hm1) + (int64_t)b * a.n_cap) : iy0;
+  const int scan_bit = 1 << (blockIdx.x & 31);
+  const int scan_none = masked ? 0 : INT_MIN;              // a word that is never a hit
+  auto is_hit = [&](int v) {                                // v: strip mask word, or the first footprint row
+    if (masked) return (v & scan_bit) != 0;
+    int d = v - r0;
     if (d < 0) d += nf;
     if (d < 0) d += nf;
     return d < rows || d + w > nf;
@@ -399,11 +420,11 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
       for (int k = sbase + tid; k < shi + lane; k += T1_SCAN * nthr) {     // warp-uniform trip count
         int yv[T1_SCAN];
 #pragma unroll
-        for (int u = 0; u < T1_SCAN; ++u) { const int s = k + u * nthr; yv[u] = s < shi ? iy0[s] : INT_MIN; }
+        for (int u = 0; u < T1_SCAN; ++u) { const int s = k + u * nthr; yv[u] = s < shi ? scan_src[s] : scan_none; }
         hits_u = 0;
 #pragma unroll
         for (int u = 0; u < T1_SCAN; ++u) {
-          const bool hit = yv[u] != INT_MIN && is_hit(yv[u]);
+          const bool hit = yv[u] != scan_none && is_hit(yv[u]);
           hits_u |= hit ? (1u << u) : 0u;
           cnt += __popc(__ballot_sync(0xffffffffu, hit));
         }
@@ -436,10 +457,10 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
       for (int k = sbase + tid; k < shi + lane; k += T1_SCAN * nthr) {
         int yv[T1_SCAN];
 #pragma unroll
-        for (int u = 0; u < T1_SCAN; ++u) { const int s = k + u * nthr; yv[u] = s < shi ? iy0[s] : INT_MIN; }
+        for (int u = 0; u < T1_SCAN; ++u) { const int s = k + u * nthr; yv[u] = s < shi ? scan_src[s] : scan_none; }
 #pragma unroll
         for (int u = 0; u < T1_SCAN; ++u) {
-          const bool hit = yv[u] != INT_MIN && is_hit(yv[u]);
+          const bool hit = yv[u] != scan_none && is_hit(yv[u]);
           const unsigned ball = __ballot_sync(0xffffffffu, hit);
           if (hit) lst_s[run + __popc(ball & ((1u << lane) - 1u))] = (unsigned short)(k + u * nthr - sbase);
           run += __popc(ball);
