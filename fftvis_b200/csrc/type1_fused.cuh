@@ -473,26 +473,37 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
     // ---- flush: evaluate kernels densely, then spread by row ownership -------------------------
     for (int c0 = 0; c0 < nh; c0 += T1_RC) {
       const int cn = min(T1_RC, nh - c0);
-      for (int t = tid; t < 2 * cn; t += nthr) {
-        const int h = t >> 1, dim = t & 1, src = sbase + (int)lst_s[c0 + h];
+      // Hit records.  Single precision: one thread per (hit, dimension, half of the kernel samples), so
+      // that the sqrt + exp evaluations of a chunk use most of the CTA's warps; double precision (fewer
+      // threads per CTA, longer evaluations): one thread per (hit, dimension).
+      constexpr bool kHalves = sizeof(T) == 4;
+      constexpr int WH = kHalves ? (WMAX + 1) / 2 : WMAX;      // samples per thread
+      for (int t = tid; t < (kHalves ? 4 : 2) * cn; t += nthr) {
+        const int hd = kHalves ? t >> 1 : t, half = kHalves ? (t & 1) : 0;
+        const int h = hd >> 1, dim = hd & 1, src = sbase + (int)lst_s[c0 + h];
         T z0;
         if (dim == 0) {
           z0 = zxp[src];
-          const int c0w = wrap_idx(ix0[src], nf);
-          rec_i0x[h] = c0w;
+          if (half == 0) {
+            rec_i0x[h] = wrap_idx(ix0[src], nf);
 #pragma unroll
-          for (int pp = 0; pp < NP; ++pp) rec_w[h * NP + pp] = Wp[(int64_t)pp * a.n_cap + src];
+            for (int pp = 0; pp < NP; ++pp) rec_w[h * NP + pp] = Wp[(int64_t)pp * a.n_cap + src];
+          }
         } else {
           z0 = zyp[src];
-          int d = iy0[src] - r0;
-          if (d < 0) d += nf;
-          if (d < 0) d += nf;
-          rec_d[h] = d;
+          if (half == 0) {
+            int d = iy0[src] - r0;
+            if (d < 0) d += nf;
+            if (d < 0) d += nf;
+            rec_d[h] = d;
+          }
         }
-        T* kk = (dim == 0 ? rec_kx : rec_ky) + h * WMAX;
+        const int jb = half * WH;
+        T* kk = (dim == 0 ? rec_kx : rec_ky) + h * WMAX + jb;
+        z0 += (T)jb;
 #pragma unroll
-        for (int j = 0; j < WMAX; ++j)
-          if (j < w) kk[j] = es_kernel<T>(z0 + (T)j, a.beta, a.c, a.halfw);
+        for (int j = 0; j < WH; ++j)
+          if (jb + j < w) kk[j] = es_kernel<T>(z0 + (T)j, a.beta, a.c, a.halfw);
       }
       __syncthreads();
       T1_PHASE(2);
