@@ -1,21 +1,23 @@
-"""Host-side astrometry for stage a1: everything that is *per time*, not
-per source.  The per-source work (3x3 rotation of Ns unit vectors, horizon cut, compaction,
-az/za) is the CUDA kernel ``fv_rotate_cut`` (csrc/rotate_cut.cuh).
+"""Host-side coordinate manager of stage a1: everything that is *per time*,
+not per source.  The per-source work (light deflection, aberration, 3x3 rotation of Ns unit
+vectors, horizon cut, compaction, az/za) is the CUDA kernel ``fv_rotate_cut`` (csrc/rotate_cut.cu).
 
 The reference obtains topocentric vectors from matvis' ``CoordinateRotationERFA`` /
 ``CoordinateRotationAstropy`` (call sites /root/reference/src/fftvis/cpu/cpu_simulate.py:693-709,
-937-940); matvis, astropy and erfa are absent from this image, so the rotation is stated here in
-closed form: Earth-rotation-angle sidereal rotation about the celestial pole followed by the
-latitude tilt.  Aberration, light deflection, precession-nutation and polar motion are NOT
-applied (SURVEY.md section 8(f) rank 2 "coordinate manager on device" is the next row that adds
-them); callers who have erfa can pass their own per-time matrices / apparent unit vectors via
-``coord_method_params={"rotation_matrices": ..., "eq_xyz": ...}``.
+937-940).  ``coordinate_blocks`` is this repo's form of that manager: ``coord_method`` selects the
+ERFA-structured model of ``core/astrometry.py`` (both matvis names map to it: they are the same
+transformation through two libraries) or the explicit Earth-rotation-only model
+(``"CoordinateRotationERA"``); ``coord_method_params`` carries matvis' ``update_bcrs_every`` plus
+the IERS quantities that cannot be looked up offline (``dut1`` seconds, ``xp`` / ``yp`` radians) and
+the escape hatches ``rotation_matrices`` / ``astrom`` / ``eq_xyz`` for callers who run erfa themselves.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
 
 import numpy as np
+
+from . import astrometry
 
 TWO_PI = 2.0 * np.pi
 
@@ -49,6 +51,19 @@ def _angle_rad(q) -> float:
     return float(q)
 
 
+def site_height(telescope_loc) -> float:
+    """Height above the WGS84 ellipsoid in metres (0 when the location does not carry one)."""
+    if isinstance(telescope_loc, TelescopeLocation):
+        return float(telescope_loc.height_m)
+    h = getattr(telescope_loc, "height", None)
+    if h is not None:
+        return float(h.to_value("m")) if hasattr(h, "to_value") else float(h)
+    if hasattr(telescope_loc, "lat"):
+        return 0.0
+    t = tuple(telescope_loc)
+    return float(t[2]) if len(t) > 2 else 0.0
+
+
 def site_lat_lon(telescope_loc) -> tuple[float, float]:
     """(lat, lon) in radians from a TelescopeLocation, an astropy EarthLocation (duck-typed:
     ``.lat``/``.lon`` angles) or a ``(lat_deg, lon_deg[, height])`` tuple."""
@@ -61,11 +76,12 @@ def site_lat_lon(telescope_loc) -> tuple[float, float]:
 
 
 def times_to_jd(times) -> np.ndarray:
-    """Julian dates (treated as UT1) from an ndarray or an astropy ``Time`` (duck-typed ``.jd``)."""
-    if hasattr(times, "ut1"):
+    """UTC Julian dates from an ndarray or an astropy ``Time`` (duck-typed ``.utc.jd`` / ``.jd``);
+    the reference wraps bare arrays as ``Time(times, format="jd")``, i.e. UTC (cpu_simulate.py:688-689)."""
+    if hasattr(times, "utc"):
         try:
-            return np.atleast_1d(np.asarray(times.ut1.jd, dtype=np.float64))
-        except Exception:  # no IERS data offline: fall through to .jd
+            return np.atleast_1d(np.asarray(times.utc.jd, dtype=np.float64))
+        except Exception:
             pass
     if hasattr(times, "jd"):
         return np.atleast_1d(np.asarray(times.jd, dtype=np.float64))
@@ -73,28 +89,42 @@ def times_to_jd(times) -> np.ndarray:
 
 
 def earth_rotation_angle(jd_ut1: np.ndarray) -> np.ndarray:
-    """IAU 2000 Earth rotation angle (radians, [0, 2pi)); JD split to keep fp64 precision."""
-    jd = np.asarray(jd_ut1, dtype=np.float64)
-    d = jd - 2451545.0
-    frac = np.mod(jd, 1.0)  # (JD - 2451545.0) mod 1: the whole-turn part of Tu drops out
-    theta = TWO_PI * np.mod(frac + 0.7790572732640 + 0.00273781191135448 * d, 1.0)
-    return np.mod(theta, TWO_PI)
+    """IAU 2000 Earth rotation angle (radians, [0, 2pi))."""
+    return astrometry.earth_rotation_angle(jd_ut1)
+
+
+def coordinate_blocks(times, telescope_loc, coord_method: str = "CoordinateRotationERFA",
+                      coord_method_params: dict | None = None) -> tuple[np.ndarray, np.ndarray | None]:
+    """Per-time blocks ``(enu_mats (nt, 3, 3), astrom (nt, 10) or None)`` handed to ``fv_rotate_cut``.
+
+    ``coord_method``: ``"CoordinateRotationERFA"`` / ``"CoordinateRotationAstropy"`` (the reference's
+    two managers, cpu_simulate.py:693; here one model: IAU 2006/2000 bias-precession-nutation, CIO
+    locator, annual + diurnal aberration, solar light deflection, polar motion) or
+    ``"CoordinateRotationERA"`` (Earth rotation angle + latitude only).  Unknown names raise
+    ``KeyError`` like the reference's ``CoordinateRotation._methods[coord_method]`` lookup."""
+    params = dict(coord_method_params or {})
+    if coord_method not in astrometry.COORD_METHODS:
+        raise KeyError(coord_method)
+    known = {"update_bcrs_every", "dut1", "xp", "yp", "rotation_matrices", "astrom", "eq_xyz"}
+    extra = set(params) - known
+    if extra:
+        raise TypeError(f"unexpected coord_method_params for {coord_method}: {sorted(extra)}")
+    if "rotation_matrices" in params:
+        mats = np.ascontiguousarray(params["rotation_matrices"], dtype=np.float64)
+        ast = params.get("astrom")
+        return mats, (None if ast is None else np.ascontiguousarray(ast, dtype=np.float64).reshape(len(mats), 10))
+    lat, lon = site_lat_lon(telescope_loc)
+    blk = astrometry.astrom_blocks(
+        times_to_jd(times), lat, lon, site_height(telescope_loc), dut1=float(params.get("dut1", 0.0)),
+        xp=float(params.get("xp", 0.0)), yp=float(params.get("yp", 0.0)),
+        update_bcrs_every=float(params.get("update_bcrs_every", 0.0)),
+        era_only=coord_method == "CoordinateRotationERA")
+    return blk["enu"], (None if coord_method == "CoordinateRotationERA" else blk["astrom"])
 
 
 def eq_to_enu_matrices(times, telescope_loc) -> np.ndarray:
-    """(ntimes, 3, 3) fp64 matrices M with  enu = M @ (cos d cos a, cos d sin a, sin d)."""
-    lat, lon = site_lat_lon(telescope_loc)
-    th = earth_rotation_angle(times_to_jd(times)) + lon
-    c, s = np.cos(th), np.sin(th)
-    sl, cl = np.sin(lat), np.cos(lat)
-    m = np.zeros((th.size, 3, 3))
-    # east
-    m[:, 0, 0], m[:, 0, 1] = -s, c
-    # north
-    m[:, 1, 0], m[:, 1, 1], m[:, 1, 2] = -sl * c, -sl * s, cl
-    # up
-    m[:, 2, 0], m[:, 2, 1], m[:, 2, 2] = cl * c, cl * s, sl
-    return m
+    """(ntimes, 3, 3) fp64 matrices of the Earth-rotation-only model: enu = M @ (cos d cos a, cos d sin a, sin d)."""
+    return coordinate_blocks(times, telescope_loc, "CoordinateRotationERA")[0]
 
 
 def equatorial_unit_vectors(ra, dec) -> np.ndarray:

@@ -16,15 +16,45 @@ constexpr int RC_THREADS = 256;
 constexpr int RC_ITEMS = 4;
 constexpr int RC_TILE = RC_THREADS * RC_ITEMS;
 
-struct Mat3 { double m[9]; };
+// Per-time rotation + the star-independent astrometry parameters (fv_astrom block of the host,
+// fftvis_b200/core/astrometry.py): Sun -> observer unit vector and distance (light deflection),
+// observer barycentric velocity / c and sqrt(1 - v^2) (annual + diurnal aberration).
+struct Mat3 { double m[9]; double eh[3], em, v[3], bm1, dlim; int on; };
+
+constexpr double kSRS = 1.97412574336e-8;   // Schwarzschild radius of the Sun (au)
+
+// ICRS unit vector -> local East-North-Up: light deflection by the Sun and aberration (the published
+// SOFA ldsun / ab arithmetic, per source), then the 3x3 of the time step.  One out-of-line copy: the
+// count and the write kernels must agree bit for bit on which sources are above the horizon.
+__device__ __noinline__ void enu_fp64(const double* __restrict__ eq, int64_t nsrc, int64_t s, const Mat3& M,
+                                      double* out) {
+  double x = eq[s], y = eq[nsrc + s], z = eq[2 * nsrc + s];
+  if (M.on) {
+    // deflection: p1 = p + w * (p x (e x p)),  w = SRS / em / max(p . (p + e), dlim)
+    const double qx = x + M.eh[0], qy = y + M.eh[1], qz = z + M.eh[2];
+    const double w = kSRS / M.em / fmax(x * qx + y * qy + z * qz, M.dlim);
+    const double cx = M.eh[1] * z - M.eh[2] * y, cy = M.eh[2] * x - M.eh[0] * z, cz = M.eh[0] * y - M.eh[1] * x;
+    const double x1 = x + w * (y * cz - z * cy), y1 = y + w * (z * cx - x * cz), z1 = z + w * (x * cy - y * cx);
+    // aberration
+    const double pdv = x1 * M.v[0] + y1 * M.v[1] + z1 * M.v[2];
+    const double w1 = 1.0 + pdv / (1.0 + M.bm1), w2 = kSRS / M.em;
+    const double ax = x1 * M.bm1 + w1 * M.v[0] + w2 * (M.v[0] - pdv * x1);
+    const double ay = y1 * M.bm1 + w1 * M.v[1] + w2 * (M.v[1] - pdv * y1);
+    const double az = z1 * M.bm1 + w1 * M.v[2] + w2 * (M.v[2] - pdv * z1);
+    const double r = 1.0 / sqrt(ax * ax + ay * ay + az * az);
+    x = ax * r; y = ay * r; z = az * r;
+  }
+  out[0] = M.m[0] * x + M.m[1] * y + M.m[2] * z;
+  out[1] = M.m[3] * x + M.m[4] * y + M.m[5] * z;
+  out[2] = M.m[6] * x + M.m[7] * y + M.m[8] * z;
+}
 
 template <typename T>
 __device__ inline void enu_of(const double* __restrict__ eq, int64_t nsrc, int64_t s, const Mat3& M,
                               T& e, T& n, T& u) {
-  const double x = eq[s], y = eq[nsrc + s], z = eq[2 * nsrc + s];
-  e = (T)(M.m[0] * x + M.m[1] * y + M.m[2] * z);
-  n = (T)(M.m[3] * x + M.m[4] * y + M.m[5] * z);
-  u = (T)(M.m[6] * x + M.m[7] * y + M.m[8] * z);
+  double o[3];
+  enu_fp64(eq, nsrc, s, M, o);
+  e = (T)o[0]; n = (T)o[1]; u = (T)o[2];
 }
 
 template <typename T>
@@ -173,11 +203,14 @@ __global__ void inplace_rot_kernel(Mat3T<T> R, T* __restrict__ b, int64_t n) {
 
 template <typename T>
 static int rotate_cut_impl(const double* eq, int64_t nsrc, int64_t lo, int64_t hi, const double* enu,
-                           const double* plane, void* xyz, void* az, void* za, int32_t* src_idx,
+                           const double* astrom, const double* plane, void* xyz, void* az, void* za, int32_t* src_idx,
                            int64_t n_cap, int32_t* n_dev, void* scratch, cudaStream_t st) {
   Mat3 M;
   Mat3T<T> P;
   for (int i = 0; i < 9; ++i) { M.m[i] = enu[i]; P.m[i] = (T)plane[i]; }
+  M.on = astrom != nullptr && astrom[9] != 0.0;
+  for (int i = 0; i < 3; ++i) { M.eh[i] = M.on ? astrom[i] : 0.0; M.v[i] = M.on ? astrom[4 + i] : 0.0; }
+  M.em = M.on ? astrom[3] : 1.0; M.bm1 = M.on ? astrom[7] : 1.0; M.dlim = M.on ? astrom[8] : 1e-6;
   const int64_t cnt = hi - lo;
   const int nblocks = (int)((cnt + RC_TILE - 1) / RC_TILE);
   int32_t* counts = (int32_t*)scratch;
@@ -202,7 +235,7 @@ extern "C" int64_t fv_rotate_cut_scratch_bytes(int64_t nsrc) {
 }
 
 extern "C" int fv_rotate_cut(int prec, const double* eq_xyz, int64_t nsrc, int64_t src_lo,
-                             int64_t src_hi, const double* enu_mat_host,
+                             int64_t src_hi, const double* enu_mat_host, const double* astrom_host,
                              const double* plane_mat_host, void* xyz, void* az, void* za,
                              int32_t* src_idx, int64_t n_cap, int32_t* n_dev, void* scratch,
                              void* stream) {
@@ -213,9 +246,9 @@ extern "C" int fv_rotate_cut(int prec, const double* eq_xyz, int64_t nsrc, int64
              "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (prec == 1)
-    return fv::rotate_cut_impl<float>(eq_xyz, nsrc, src_lo, src_hi, enu_mat_host, plane_mat_host, xyz,
+    return fv::rotate_cut_impl<float>(eq_xyz, nsrc, src_lo, src_hi, enu_mat_host, astrom_host, plane_mat_host, xyz,
                                       az, za, src_idx, n_cap, n_dev, scratch, st);
-  return fv::rotate_cut_impl<double>(eq_xyz, nsrc, src_lo, src_hi, enu_mat_host, plane_mat_host, xyz,
+  return fv::rotate_cut_impl<double>(eq_xyz, nsrc, src_lo, src_hi, enu_mat_host, astrom_host, plane_mat_host, xyz,
                                      az, za, src_idx, n_cap, n_dev, scratch, st);
 }
 

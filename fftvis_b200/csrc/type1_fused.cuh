@@ -556,9 +556,12 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
           if (L > 0) load_rec(0);
           for (int r = 0; r < L; ++r) {
             // this hit's cells
-            int rr = d < rows ? d : d - nf;                  // first footprint row relative to the strip (may be < 0)
-            rr += jrow;
-            const bool row_ok = lane_on && (unsigned)rr < (unsigned)rows;
+            // this lane's footprint row relative to the strip, wrapped at nf (d is in [0, nf)): a footprint
+            // that starts below the strip's end and runs past the grid edge re-enters the strip at row 0
+            // (whole-grid strips, or a short last strip), so the wrap is applied per lane, not per hit
+            int rr = d + jrow;
+            if (rr >= nf) rr -= nf;
+            const bool row_ok = lane_on && rr < rows;
             const unsigned a_row = a_strip + (unsigned)(rr * pitch) * (unsigned)sizeof(C);
             unsigned ca[CPL];
             bool ok[CPL];

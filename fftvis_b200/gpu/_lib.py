@@ -44,7 +44,7 @@ _SIGNATURES = {
     "fv_next235even": (c_int64, [c_int64]),
     "fv_rotate_cut_scratch_bytes": (c_int64, [c_int64]),
     "fv_rotate_cut": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, POINTER(c_double),
-                              POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                              POINTER(c_double), POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                               c_void_p, c_void_p, c_void_p]),
     "fv_inplace_rot": (c_int, [c_int, POINTER(c_double), c_void_p, c_int64, c_void_p]),
     "fv_weights": (c_int, [c_int, c_int, POINTER(fv_beam), POINTER(fv_beam), c_void_p, c_void_p,

@@ -18,6 +18,32 @@ _RDT = {1: torch.float32, 2: torch.float64}
 _CDT = {1: torch.complex64, 2: torch.complex128}
 
 
+INTERPOLATION_FUNCTIONS = ("az_za_map_coordinates", "az_za_simple")
+
+
+def resolve_interpolation(interpolation_function, spline_opts) -> int:
+    """Spline order the device evaluates for the reference's ``interpolation_function`` +
+    ``spline_opts`` (passed to pyuvdata at cpu/beams.py:69-74).
+
+    ``az_za_map_coordinates``: ``spline_opts["order"]`` (``scipy.ndimage.map_coordinates``); 1 when
+    absent.  ``az_za_simple``: ``RectBivariateSpline(kx, ky)``; ``kx = ky = 1`` is the same bilinear
+    interpolant as order 1 (the identity the reference tests at tests/test_cpu_beams.py:15-87) and is
+    evaluated as such, other degrees (FITPACK's not-a-knot splines) raise ``NotImplementedError``.
+    Unknown names raise ``ValueError``; nothing is silently ignored."""
+    opts = dict(spline_opts or {})
+    if interpolation_function not in INTERPOLATION_FUNCTIONS:
+        raise ValueError(f"unknown interpolation_function {interpolation_function!r}; "
+                         f"expected one of {INTERPOLATION_FUNCTIONS}")
+    if interpolation_function == "az_za_simple":
+        kx, ky = int(opts.get("kx", 1)), int(opts.get("ky", 1))
+        if (kx, ky) != (1, 1):
+            raise NotImplementedError(
+                "interpolation_function='az_za_simple' is evaluated on the GPU for kx = ky = 1 (bilinear) only; "
+                f"got kx={kx}, ky={ky}")
+        return 1
+    return int(opts.get("order", 1))
+
+
 class DeviceBeam:
     """A beam model uploaded to the GPU (owns the table tensor) + its ``fv_beam`` descriptor."""
 
@@ -146,16 +172,17 @@ class GPUBeamEvaluator(BeamEvaluator):
                       interpolation_function="az_za_map_coordinates"):
         """Beam response at (az, za) for one frequency: ``(2, 2, n)`` complex E-field
         [vector component, feed, source] if ``polarized`` else ``(n,)`` power.  Host arrays in and
-        out like the CPU evaluator (cpu/beams.py:12-89); ``interpolation_function`` other than
-        the map-coordinates one is accepted and evaluated the same way at order <= 1."""
+        out like the CPU evaluator (cpu/beams.py:12-89); ``interpolation_function`` and
+        ``spline_opts`` are resolved by ``resolve_interpolation`` (unsupported choices raise)."""
         _lib.require_gpu()
         self.polarized = polarized
         self.freq = freq
         self.spline_opts = spline_opts or {}
+        order = resolve_interpolation(interpolation_function, self.spline_opts)
         az = np.asarray(az)
         prec = 1 if az.dtype == np.float32 else 2
         n = az.size
-        ob = evaluate_beam_device(beam, az, za, polarized, freq, prec, int(self.spline_opts.get("order", 1)))
+        ob = evaluate_beam_device(beam, az, za, polarized, freq, prec, order)
         res = ob.cpu().numpy()
         interp_beam = res.reshape(2, 2, n) if polarized else res[0].real.astype(az.dtype)
         if check:

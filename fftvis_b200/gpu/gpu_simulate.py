@@ -35,7 +35,7 @@ from ..core import antenna_gridding, catalog, coords
 from ..core import utils as core_utils
 from ..core.simulate import SimulationEngine, default_accuracy_dict
 from . import _lib
-from .beams import DeviceBeam, GPUBeamEvaluator, launch_weights
+from .beams import DeviceBeam, GPUBeamEvaluator, launch_weights, resolve_interpolation
 from .nufft import ModeSet, NufftPlan, default_plan
 
 logger = logging.getLogger(__name__)
@@ -83,6 +83,7 @@ class SimulationPlan:
     f_lo: int
     f_hi: int
     enu_mats: np.ndarray               # (nt, 3, 3) fp64
+    astrom: np.ndarray | None          # (nt, 10) fp64 deflection / aberration block (None: rotation only)
     plane_mat: np.ndarray              # (3, 3) working precision, as fp64
     eq_xyz: torch.Tensor               # (3, nsrc) fp64
     flux: torch.Tensor                 # (nf_total, nsrc) or (nf_total, 4, nsrc) cplx
@@ -151,7 +152,8 @@ class GPUSimulationEngine(SimulationEngine):
                 baselines=None, beam_idx=None, precision=2, polarized=False, eps=None,
                 upsample_factor=2, beam_spline_opts=None, flat_array_tol=1e-6,
                 coord_method_params=None, force_use_type3=False, nchunks=1, source_buffer=1.0,
-                beam_coefs=None, freq_range=None) -> SimulationPlan:
+                beam_coefs=None, freq_range=None, coord_method="CoordinateRotationERFA",
+                interpolation_function="az_za_map_coordinates") -> SimulationPlan:
         """Host front half of ``simulate`` (cpu_simulate.py:583-709) + upload of every input.
         ``freq_range=(lo, hi)`` restricts the plan to that slice of ``freqs`` (one rank's shard)."""
         dev = self._device()
@@ -212,10 +214,7 @@ class GPUSimulationEngine(SimulationEngine):
 
         # ---- per-time rotation matrices (stage a1, host part)
         params = dict(coord_method_params or {})
-        if "rotation_matrices" in params:
-            enu_mats = np.ascontiguousarray(params["rotation_matrices"], dtype=np.float64)
-        else:
-            enu_mats = coords.eq_to_enu_matrices(times, telescope_loc)
+        enu_mats, astrom = coords.coordinate_blocks(times, telescope_loc, coord_method, params)
         eq = params.get("eq_xyz")
         if eq is None:
             eq = coords.equatorial_unit_vectors(ra, dec)
@@ -242,7 +241,7 @@ class GPUSimulationEngine(SimulationEngine):
                 del half
             freqs_d = torch.as_tensor(freqs.astype(np.float64)).to(dev)
 
-            order = int((beam_spline_opts or {}).get("order", 1))
+            order = resolve_interpolation(interpolation_function, beam_spline_opts)
             models = []
             for b in beam_list:
                 m = as_beam_model(b)
@@ -287,7 +286,7 @@ class GPUSimulationEngine(SimulationEngine):
             precision=precision, polarized=polarized, polarized_sky=pol_sky, nfeeds=2 if polarized else 1,
             eps=float(eps), upsample_factor=float(upsample_factor), use_type1=is_gridded,
             is_coplanar=is_coplanar, n_modes=n_modes, nbls=nbls, nsrc=nsrc, nchunks=nchunks, n_cap=n_cap,
-            freqs_host=freqs, f_lo=f_lo, f_hi=f_hi, enu_mats=enu_mats,
+            freqs_host=freqs, f_lo=f_lo, f_hi=f_hi, enu_mats=enu_mats, astrom=astrom,
             plane_mat=np.ascontiguousarray(plane, dtype=np.float64), eq_xyz=eq_d, flux=flux_d,
             freqs_dev=freqs_d, beams=dbeams, pairs=pairs, basis=basis, freq_batch=int(fb), device=dev)
 
@@ -418,7 +417,9 @@ class GPUSimulationEngine(SimulationEngine):
                         continue
                     _lib.check(L.fv_rotate_cut(
                         prec, plan.eq_xyz.data_ptr(), plan.nsrc, lo, hi,
-                        _lib.doubles(plan.enu_mats[ti].ravel()), _lib.doubles(plan.plane_mat.ravel()),
+                        _lib.doubles(plan.enu_mats[ti].ravel()),
+                        _lib.doubles(plan.astrom[ti]) if plan.astrom is not None else None,
+                        _lib.doubles(plan.plane_mat.ravel()),
                         w["xyz"].data_ptr(), w["az"].data_ptr(), w["za"].data_ptr(),
                         w["src_idx"].data_ptr(), plan.n_cap, w["n_dev"].data_ptr(),
                         w["scratch"].data_ptr(), st.cuda_stream), "fv_rotate_cut")
@@ -517,13 +518,16 @@ class GPUSimulationEngine(SimulationEngine):
         """Simulate visibilities on the GPU; same parameters and return value as the CPU engine
         (cpu_simulate.py:537-569, return at :850-854).  ``nprocesses``, ``nthreads``,
         ``force_use_ray``, ``trace_mem`` and ``enable_memory_monitor`` are CPU-only knobs and are
-        accepted and ignored; ``coord_method`` selects nothing here (see core/coords.py)."""
+        accepted and ignored.  ``coord_method`` / ``coord_method_params`` select the coordinate model
+        (core/coords.py ``coordinate_blocks``; unknown names raise ``KeyError`` as in the reference);
+        ``interpolation_function`` is validated by ``gpu/beams.py`` (never silently ignored)."""
         plan = self.prepare(ants, freqs, fluxes, beam_list, ra, dec, times, telescope_loc,
                             baselines=baselines, beam_idx=beam_idx, precision=precision,
                             polarized=polarized, eps=eps, upsample_factor=upsample_factor,
                             beam_spline_opts=beam_spline_opts, flat_array_tol=flat_array_tol,
                             coord_method_params=coord_method_params, force_use_type3=force_use_type3,
-                            nchunks=nchunks, source_buffer=source_buffer, beam_coefs=beam_coefs)
+                            nchunks=nchunks, source_buffer=source_buffer, beam_coefs=beam_coefs,
+                            coord_method=coord_method, interpolation_function=interpolation_function)
         host = self._pinned_result(plan)
         out = self.run_plan(plan, host_out=host)
         if host is None:

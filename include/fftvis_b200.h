@@ -59,7 +59,13 @@ int64_t fv_next235even(int64_t n);
  * Replaces coord_mgr.rotate(ti) + select_chunk (cpu_simulate.py:937-946), enu_to_az_za
  * (:957-959), inplace_rot (cpu/utils.py:5-24; calls :961-965) and topo *= 2*pi (:967).
  *   eq_xyz     (3, nsrc) fp64 equatorial unit vectors
- *   enu_mat    9 fp64, row-major: enu = M @ eq       (per time; core/coords.py)
+ *   enu_mat    9 fp64, row-major: enu = M @ p        (per time; core/astrometry.py: latitude tilt .
+ *              polar motion . R3(local Earth rotation angle) . celestial-to-intermediate matrix)
+ *   astrom     NULL, or 10 fp64 per time (matvis CoordinateRotationERFA's apco block, cpu_simulate.py:
+ *              693-709): Sun->observer unit vector [3], its length in au, observer barycentric
+ *              velocity / c [3], sqrt(1 - v^2), deflection limiter, flag (0: skip).  When present every
+ *              source direction gets the Sun's light deflection and the aberration before M
+ *              (erfa ldsun + ab arithmetic, in fp64), i.e. p above is the proper direction.
  *   plane_mat  9 fp64, row-major: rotation R (type 3) or basis_matrix^T / c (type 1);
  *              applied in working precision in the reference's operation order, then * 2 pi
  *   src_lo/hi  catalogue slice [lo, hi) handled by this call (the reference's `nchunks`)
@@ -71,9 +77,9 @@ int64_t fv_next235even(int64_t n);
  */
 int64_t fv_rotate_cut_scratch_bytes(int64_t nsrc);
 int fv_rotate_cut(int prec, const double* eq_xyz, int64_t nsrc, int64_t src_lo, int64_t src_hi,
-                  const double* enu_mat_host, const double* plane_mat_host, void* xyz, void* az,
-                  void* za, int32_t* src_idx, int64_t n_cap, int32_t* n_dev, void* scratch,
-                  void* stream);
+                  const double* enu_mat_host, const double* astrom_host, const double* plane_mat_host,
+                  void* xyz, void* az, void* za, int32_t* src_idx, int64_t n_cap, int32_t* n_dev,
+                  void* scratch, void* stream);
 
 /* in-place b[:, s] <- rot @ b[:, s]  (gpu/utils.py:8 `inplace_rot`; cpu/utils.py:5-24) */
 int fv_inplace_rot(int prec, const double* rot_host, void* b /* (3, n) real */, int64_t n,

@@ -23,13 +23,13 @@ from __future__ import annotations
 
 import numpy as np
 
-from fftvis_b200.core import antenna_gridding as _grid
-from fftvis_b200.core import catalog as _catalog
-from fftvis_b200.core import coords as _coords
-from fftvis_b200.core import utils as _utils
-
 from . import beams as obeams
+from . import coords as _coords
+from . import host_ref as _utils        # reference modules by path where present, else the private restatement
 from . import nufft_cpu
+
+_grid = _utils
+_catalog = _utils
 
 C_LIGHT = 299792458.0
 DEFAULT_EPS = {1: 6e-8, 2: 1e-13}     # reference core/simulate.py:16-19
@@ -39,12 +39,13 @@ def _dtypes(precision):
     return (np.float32, np.complex64) if precision == 1 else (np.float64, np.complex128)
 
 
-def topocentric(ra, dec, times, telescope_loc, precision=2):
-    """Per-time ENU unit vectors (nt, 3, Ns) in the working real dtype, computed in fp64."""
+def topocentric(ra, dec, times, telescope_loc, precision=2, coord_method="CoordinateRotationERFA",
+                coord_method_params=None):
+    """Per-time ENU unit vectors (nt, 3, Ns) in the working real dtype, computed in fp64 from the
+    dtype-cast ra/dec (oracle/coords.py: the oracle's own chain)."""
     rd, _ = _dtypes(precision)
-    eq = _coords.equatorial_unit_vectors(np.asarray(ra, rd), np.asarray(dec, rd))
-    mats = _coords.eq_to_enu_matrices(times, telescope_loc)
-    return np.einsum("tij,js->tis", mats, eq).astype(rd)
+    return _coords.topocentric_enu(np.asarray(ra, rd), np.asarray(dec, rd), times, telescope_loc,
+                                   coord_method, coord_method_params).astype(rd)
 
 
 def prepare_beam_evaluation(antnums, baselines, beam_idx):
@@ -76,12 +77,12 @@ def _evaluate_beams(beam_list, az, za, polarized, freq, fidx, spline_opts, cdtyp
 def simulate_direct(ants, fluxes, ra, dec, freqs, times, beam_list, telescope_loc,
                     baselines=None, beam_idx=None, precision=2, polarized=False,
                     beam_spline_opts=None, beam_coefs=None, reference_flip_quirk=True,
-                    nthreads=None):
+                    nthreads=None, coord_method="CoordinateRotationERFA", coord_method_params=None):
     """Direct fp64 evaluation of the measurement equation on the dtype-cast inputs.
     Returns (nf, nt, nbls) or (nf, nt, 2, 2, nbls) complex128."""
     rd, _ = _dtypes(precision)
     freqs = np.asarray(freqs).astype(rd).astype(np.float64)
-    nf, nt = freqs.size, len(_coords.times_to_jd(times))
+    nf, nt = freqs.size, len(_coords.jd_of(times))
     ants = {k: np.asarray(v, dtype=float) for k, v in ants.items()}
     antnums = list(ants.keys())
     if baselines is None:
@@ -94,7 +95,8 @@ def simulate_direct(ants, fluxes, ra, dec, freqs, times, beam_list, telescope_lo
     antvecs = np.array([ants[a] for a in antnums]).astype(rd).astype(np.float64)
     a_index = {a: i for i, a in enumerate(antnums)}
     blvec = np.array([antvecs[a_index[b[1]]] - antvecs[a_index[b[0]]] for b in baselines])  # (nbls,3)
-    topo_all = topocentric(ra, dec, times, telescope_loc, precision).astype(np.float64)
+    topo_all = topocentric(ra, dec, times, telescope_loc, precision, coord_method,
+                           coord_method_params).astype(np.float64)
     nfeed = 2 if polarized else 1
     vis = np.zeros((nt, nbls, nfeed, nfeed, nf), np.complex128)
 
@@ -198,7 +200,8 @@ def _run_nufft(app, topo, uvw, bls, flipped, idx, use_type1, is_coplanar, tx, ty
 def simulate_cpu(ants, fluxes, ra, dec, freqs, times, beam_list, telescope_loc, baselines=None,
                  beam_idx=None, precision=2, polarized=False, eps=None, upsample_factor=2,
                  beam_spline_opts=None, flat_array_tol=1e-6, force_use_type3=False,
-                 beam_coefs=None, nthreads=None, direct=False, freq_slice=None, time_slice=None):
+                 beam_coefs=None, nthreads=None, direct=False, freq_slice=None, time_slice=None,
+                 coord_method="CoordinateRotationERFA", coord_method_params=None):
     """Reference-structured CPU pipeline (see module docstring).  ``direct=True`` swaps the
     NUFFT for the fp64 direct sum while keeping every other step (casts, rotation, gridding)."""
     rd, cd = _dtypes(precision)
@@ -216,7 +219,7 @@ def simulate_cpu(ants, fluxes, ra, dec, freqs, times, beam_list, telescope_loc, 
     plan = plan_array(ants, baselines, precision, flat_array_tol, force_use_type3)
     rot, bls, antnums = plan["rotation_matrix"], plan["bls"], plan["antnums"]
     use_type1, is_coplanar, basis = plan["is_gridded"], plan["is_coplanar"], plan["basis_matrix"]
-    topo_all = topocentric(ra, dec, times, telescope_loc, precision)
+    topo_all = topocentric(ra, dec, times, telescope_loc, precision, coord_method, coord_method_params)
     nt = topo_all.shape[0]
     t_idx = range(nt)[time_slice or slice(None)]
     f_idx = range(freqs.size)[freq_slice or slice(None)]
