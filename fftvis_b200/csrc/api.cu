@@ -33,8 +33,21 @@ extern "C" int fv_memcpy2d_async(void* dst, int64_t dpitch, const void* src, int
   FV_REQUIRE(dst && src, "null pointer");
   FV_REQUIRE(width >= 0 && height >= 0 && dpitch >= width && spitch >= width, "bad pitch / extent");
   if (width == 0 || height == 0) return FV_OK;
-  FV_CUDA(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height,
-                            direction == 0 ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice,
-                            (cudaStream_t)stream));
+  const cudaMemcpyKind kind = direction == 0 ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+  // cudaMemcpy2DAsync rejects pitches above cudaDevAttrMaxPitch (2 GiB - 1): rows that far apart
+  // (e.g. nt * P * nbls * 16 B of a long observation) go as one contiguous copy per row instead
+  int dev = 0, max_pitch = 0;
+  FV_CUDA(cudaGetDevice(&dev));
+  FV_CUDA(cudaDeviceGetAttribute(&max_pitch, cudaDevAttrMaxPitch, dev));
+  if (dpitch == width && spitch == width) {
+    FV_CUDA(cudaMemcpyAsync(dst, src, (size_t)width * (size_t)height, kind, (cudaStream_t)stream));
+  } else if (dpitch > (int64_t)max_pitch || spitch > (int64_t)max_pitch) {
+    for (int64_t r = 0; r < height; ++r)
+      FV_CUDA(cudaMemcpyAsync((char*)dst + r * dpitch, (const char*)src + r * spitch, (size_t)width, kind,
+                              (cudaStream_t)stream));
+  } else {
+    FV_CUDA(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height, kind,
+                              (cudaStream_t)stream));
+  }
   return FV_OK;
 }

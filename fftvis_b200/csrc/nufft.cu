@@ -208,6 +208,12 @@ extern "C" int fv_modeset_destroy(fv_modeset* M) {
   return FV_OK;
 }
 
+extern "C" int fv_plan_last_geometry(fv_plan* P, int64_t* out12_host) {
+  FV_REQUIRE(P && out12_host, "null pointer");
+  for (int i = 0; i < 12; ++i) out12_host[i] = P->last_geo[i];
+  return FV_OK;
+}
+
 extern "C" int fv_plan_set_option(fv_plan* P, const char* name, int64_t value) {
   FV_REQUIRE(P && name, "null pointer");
   const std::string n(name);

@@ -472,6 +472,8 @@ struct fv_plan {
   int t3_v[3] = {0, 0, 0}, t3_thr[3] = {0, 0, 0}; // tuning overrides: vectors per CTA / threads of the x, y, z passes
   int t1_rows = 0;                               // strip height override (0 = automatic)
   int t1_cols = 0;                               // columns per CTA override (0 = automatic)
+  // geometry of the last type-3 transform: dim, w, nf[3] (spread grid), ng[3] (FFT grid), tiled, own_fft, sub-batch
+  int64_t last_geo[12] = {0};
 };
 
 // baselines of one beam pair as integer modes, bucketed by first mode number (fused type-1 path)

@@ -66,6 +66,7 @@ _SIGNATURES = {
                                   POINTER(c_double), c_int, c_int, c_void_p, c_void_p, c_double, c_double,
                                   POINTER(fv_epilogue)]),
     "fv_plan_set_option": (c_int, [c_void_p, c_char_p, c_int64]),
+    "fv_plan_last_geometry": (c_int, [c_void_p, POINTER(c_int64)]),
     "fv_nufft3": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                           POINTER(c_double), c_void_p, c_void_p, c_void_p, c_int64,
                           POINTER(c_double), POINTER(c_double), c_int, c_int, c_void_p, c_double,

@@ -364,14 +364,24 @@ class GPUSimulationEngine(SimulationEngine):
         return w
 
     def run_plan(self, plan: SimulationPlan, out: torch.Tensor | None = None,
-                 time_range=None, host_out: torch.Tensor | None = None) -> torch.Tensor:
+                 time_range=None, host_out: torch.Tensor | None = None, slab_hook=None) -> torch.Tensor:
         """Device-only hot loop (the GPU form of ``_evaluate_vis_chunk``, cpu_simulate.py:936-1069).
         Returns the device tensor ``(nf_local, nt, P, nbls)`` in the final output layout.
 
-        ``host_out``: a page-locked host tensor of the same shape.  When given, every finished time
-        slab ``out[:, t]`` is copied into it on a second stream (``fv_memcpy2d_async``) while the next
-        time steps are computed -- the device form of the reference's ``vis[tc][..., fc] = future``
-        scatter (cpu_simulate.py:846-847); the caller synchronises the device before reading it."""
+        ``out``: where to write.  Any view shaped ``(nf_local, nt, P, nbls)`` whose last two axes are
+        contiguous; the frequency and time strides are free, so the same loop fills the reference's
+        frequency-major array, a time-major ``(nt, nf_local, P, nbls)`` buffer (``buf.permute(1, 0, 2,
+        3)``: every time slab contiguous, ready for a send) or this rank's frequency block inside the
+        gathered array of all ranks (gpu/distributed.py).
+
+        ``host_out``: a page-locked host tensor ``(nf_local, nt, P, nbls)``, contiguous.  When given,
+        every finished time slab ``out[:, t]`` is copied into it on a second stream
+        (``fv_memcpy2d_async``) while the next time steps are computed -- the device form of the
+        reference's ``vis[tc][..., fc] = future`` scatter (cpu_simulate.py:846-847); the caller
+        synchronises the device before reading it.
+
+        ``slab_hook(to)``: called after all work of time slab ``to`` has been enqueued on the current
+        stream (the sharded driver posts that slab's NCCL transfer there)."""
         dev, prec = plan.device, plan.precision
         L = _lib.lib()
         P = 4 if plan.polarized else 1
@@ -388,10 +398,17 @@ class GPUSimulationEngine(SimulationEngine):
             if out is None:
                 out = torch.zeros((nfl, nt, P, plan.nbls), dtype=cdt, device=dev)
             else:
+                if tuple(out.shape) != (nfl, nt, P, plan.nbls) or out.dtype != cdt:
+                    raise ValueError(f"out must be {(nfl, nt, P, plan.nbls)} {cdt}")
+                if out.numel() and (out.stride(3) != 1 or out.stride(2) != plan.nbls):
+                    raise ValueError("the last two axes (P, nbls) of out must be contiguous")
                 out.zero_()
             if nfl == 0 or nt == 0 or plan.nbls == 0 or plan.nsrc == 0:
                 if host_out is not None:
                     host_out.zero_()
+                if slab_hook is not None:
+                    for to in range(nt):
+                        slab_hook(to)
                 return out
             w = self._workspace(plan)
             esz = out.element_size()
@@ -403,14 +420,12 @@ class GPUSimulationEngine(SimulationEngine):
             copy_st = None
             if host_out is not None:
                 if tuple(host_out.shape) != tuple(out.shape) or host_out.dtype != out.dtype \
-                        or not host_out.is_contiguous() or not out.is_contiguous():
+                        or not host_out.is_contiguous():
                     raise ValueError("host_out must be a contiguous host tensor shaped and typed like the result")
                 copy_st = _copy_stream(dev)
                 copy_st.wait_stream(st)                      # the zero fill precedes every slab copy
-            slab = P * plan.nbls * esz
+            s_f, s_t = out.stride(0), out.stride(1)          # in elements
             for to, ti in enumerate(range(t_lo, t_hi)):
-                if to > 0 and copy_st is not None:
-                    self._stream_slab(out, host_out, to - 1, nfl, nt, slab, st, copy_st)
                 for ch in range(plan.nchunks):
                     lo, hi = ch * chunk, min(plan.nsrc, (ch + 1) * chunk)
                     if lo >= hi:
@@ -437,8 +452,8 @@ class GPUSimulationEngine(SimulationEngine):
                     for f0 in range(plan.f_lo, plan.f_hi, plan.freq_batch):
                         nb = min(plan.freq_batch, plan.f_hi - f0)
                         scale = freqs64[f0:f0 + nb]
-                        obase = out.data_ptr() + ((f0 - plan.f_lo) * nt + to) * P * plan.nbls * esz
-                        sb_, sp_ = nt * P * plan.nbls, plan.nbls
+                        obase = out.data_ptr() + ((f0 - plan.f_lo) * s_f + to * s_t) * esz
+                        sb_, sp_ = s_f, plan.nbls
                         if plan.basis is not None:
                             self._basis_batch(plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st)
                             continue
@@ -450,19 +465,25 @@ class GPUSimulationEngine(SimulationEngine):
                                 obase, sb_, sp_, pmap, pt.kmap.data_ptr() if pt.kmap is not None else 0,
                                 pt.conj.data_ptr() if pt.conj is not None else 0, accumulate=True)
                             self._nufft_batch(plan, w, nufft, pt, dim, xlim, scale, nb, epi)
+                if copy_st is not None:
+                    self._stream_slab(out, host_out, to, st, copy_st)
+                if slab_hook is not None:
+                    slab_hook(to)
             if copy_st is not None:
-                self._stream_slab(out, host_out, nt - 1, nfl, nt, slab, st, copy_st)
                 st.wait_stream(copy_st)                      # `out` may be reused once the copies are done
             return out
 
     @staticmethod
-    def _stream_slab(out, host_out, to, nfl, nt, slab, st, copy_st):
-        """Enqueue the D2H of time slab ``to`` (nf rows of ``slab`` bytes, ``nt * slab`` apart) behind
-        the work enqueued so far."""
+    def _stream_slab(out, host_out, to, st, copy_st):
+        """Enqueue the D2H of time slab ``to`` (nf rows of P * nbls elements; rows ``out.stride(0)``
+        apart on the device, ``nt`` slabs apart on the host) behind the work enqueued so far."""
+        esz = out.element_size()
+        nfl, nt = out.shape[0], out.shape[1]
+        slab = out.shape[2] * out.shape[3] * esz
         copy_st.wait_stream(st)
         _lib.check(_lib.lib().fv_memcpy2d_async(
-            host_out.data_ptr() + to * slab, nt * slab, out.data_ptr() + to * slab, nt * slab, slab, nfl,
-            0, copy_st.cuda_stream), "fv_memcpy2d_async")
+            host_out.data_ptr() + to * slab, nt * slab, out.data_ptr() + to * out.stride(1) * esz,
+            out.stride(0) * esz, slab, nfl, 0, copy_st.cuda_stream), "fv_memcpy2d_async")
 
     def _nufft_batch(self, plan, w, nufft, pt, dim, xlim, scale, nb, epi):
         W = w["W"][:nb]

@@ -94,6 +94,17 @@ class NufftPlan:
             out[name] = (ms.value, cnt.value)
         return out
 
+    def last_type3_geometry(self) -> dict | None:
+        """Grid geometry of the last type-3 transform of this plan (None before the first)."""
+        g = (ctypes.c_int64 * 12)()
+        _lib.check(_lib.lib().fv_plan_last_geometry(self._h, g))
+        if g[0] == 0:
+            return None
+        dim = int(g[0])
+        nf, ng = [int(g[2 + d]) for d in range(dim)], [int(g[5 + d]) for d in range(dim)]
+        return dict(dim=dim, w=int(g[1]), nf=nf, ng=ng, G1=int(np.prod(nf)), G2=int(np.prod(ng)),
+                    tiles=bool(g[8]), own_fft=bool(g[9]), sub_batch=int(g[10]), ntr=int(g[11]))
+
     def bytes(self) -> int:
         return int(_lib.lib().fv_plan_bytes(self._h))
 

@@ -197,6 +197,11 @@ int fv_nufft2d1_fused(fv_plan* plan, int prec, const void* bx, const void* by, c
 /* tuning knobs: "t1_rows" (strip height of the fused type-1 path, 0 = automatic), "t1_cols"
  * (columns per CTA of its second pass), "max_grid_bytes" */
 int fv_plan_set_option(fv_plan* plan, const char* name, int64_t value);
+/* Geometry of the plan's last type-3 transform, for the roofline of bench.py (finufft keeps the same
+ * numbers inside its plan object: nf1..3, the inner type-2 plan's grid; cpu/nufft.py:48,105 never
+ * sees them): out12 = {dim, w, nf[3] spread grid, ng[3] FFT grid, tiled spreader?, own pruned FFT?,
+ * frequencies per sub-batch, ntr}. */
+int fv_plan_last_geometry(fv_plan* plan, int64_t* out12_host);
 
 /* type 3, 2-D / 3-D (cpu_nufft2d / cpu_nufft3d -> finufft.nufft2d3 / nufft3d3, cpu/nufft.py:11-118),
  * batched over nb frequencies:   s_k(b) = fl(base_k * scale[b])   (uvw = bls*freq, :973)

@@ -352,6 +352,11 @@ def topocentric_enu(ra, dec, times, telescope_loc, coord_method="CoordinateRotat
     jds = jd_of(times)
     out = np.empty((jds.size, 3, ra.size))
     p0 = np.stack([np.cos(dec) * np.cos(ra), np.cos(dec) * np.sin(ra), np.sin(dec)])
+    if "rotation_matrices" in prm:
+        # the caller's own per-time equatorial -> ENU matrices (the engine's escape hatch for users who run
+        # erfa themselves): a plain rotation of the catalogue vectors
+        mats = np.asarray(prm["rotation_matrices"], dtype=np.float64).reshape(jds.size, 3, 3)
+        return np.einsum("tij,js->tis", mats, p0)
     upd = float(prm.get("update_bcrs_every", 0.0))
     held, held_jd = None, None
     for i, jd in enumerate(jds):
@@ -370,6 +375,18 @@ def topocentric_enu(ra, dec, times, telescope_loc, coord_method="CoordinateRotat
             ri, di = held
         out[i] = atioq_enu(ri, di, ast)
     return out
+
+
+def rotation_matrices(times, telescope_loc, coord_method="CoordinateRotationERA", coord_method_params=None):
+    """(nt, 3, 3) equatorial -> ENU matrices of this module's chain for the rotation-only part of
+    ``coord_method`` (its action on the three coordinate axes, with no aberration / deflection): lets a
+    test hand the SAME per-time rotation to the engine and to the direct sum, so that what is compared is
+    the transform and not two roundings of the Earth rotation angle (a 1e-15 rad difference in the
+    rotation is 2 pi f |b| / c ~ 1e3 times larger in the phase of a 300 m baseline at 200 MHz)."""
+    ra = np.array([0.0, np.pi / 2, 0.0])
+    dec = np.array([0.0, 0.0, np.pi / 2])
+    enu = topocentric_enu(ra, dec, times, telescope_loc, coord_method, coord_method_params)   # (nt, 3, 3): columns
+    return np.ascontiguousarray(enu)
 
 
 def enu_to_az_za(enu_e, enu_n, orientation="uvbeam"):

@@ -18,3 +18,13 @@ def small_sky(nsrc, freqs, seed=42, polarized=False):
 
 
 TIMES = np.array([2459845.0, 2459845.0 + 600 / 86400.0])
+
+
+F32_EPS = 6e-8
+
+
+def f32_bar(cpu, want, eps=F32_EPS, slack=1.5):
+    """fp32 parity bar: north_star's 10 x eps, or -- where the rounding of the fp32 *inputs* (phases of
+    tens of radians) already exceeds that -- ``slack`` x the error the CPU restatement makes in the same
+    precision on the same inputs.  No constant floor: a regression against the CPU path fails."""
+    return max(10 * eps, slack * relerr(cpu, want))

@@ -140,3 +140,77 @@ def test_basis_simulation_matches_per_antenna_simulation(different):
     err = relerr(vis_basis, vis_ref)
     print("basis vs analytic relerr", err)
     assert err < 1e-4
+
+
+# ---- against numpy.linalg.svd of ORACLE-evaluated beams (reference core/beam_basis.py:128-151) -----
+@pytest.mark.gpu
+@pytest.mark.parametrize("polarized", [True, False])
+def test_singular_values_and_subspace_match_numpy_svd_of_oracle_beams(polarized):
+    """The device QR + SVD against the reference's own recipe done on the CPU: beams evaluated by the
+    oracle's numpy beam models on the common grid, flattened, ``numpy.linalg.svd(full_matrices=False)``,
+    ``s / s[0] >= threshold`` (core/beam_basis.py:128-151).  Compared: the number of retained
+    eigenbeams, the singular values (= column norms of ``beam_coefs``), the spanned subspace (the
+    singular vectors themselves are defined up to a phase) and the reconstructed beams."""
+    from fftvis_b200 import AiryBeam, GaussianBeam, compute_beam_basis, synth
+    from fftvis_b200.beam_models import as_beam_model
+    from oracle import beams as obeams
+    n1, n2 = 91, 46
+    axis1, axis2 = np.linspace(0.0, 2 * np.pi, n1), np.linspace(0.0, np.pi, n2)
+    analytic = [AiryBeam(diameter=14.0), AiryBeam(diameter=13.0), GaussianBeam(diameter=14.0),
+                GaussianBeam(diameter=12.0), AiryBeam(diameter=14.0)]            # rank 4 of 5
+    tables = [synth.synthetic_uvbeam([_FREQ], naz=90, nza=46, seed=s, perturb=0.3) for s in range(3)]
+    beam_list = analytic + (tables if polarized else [])
+    eb, coefs = compute_beam_basis(beam_list, freq=_FREQ, polarized=polarized, threshold=1e-10,
+                                   axis1_array=axis1, axis2_array=axis2)
+    az, za = np.tile(axis1, n2), np.repeat(axis2, n1)
+    rows = []
+    for b in beam_list:
+        m = as_beam_model(b)
+        if not polarized:
+            m = m.to_power()
+        r = obeams.evaluate_beam(m, az, za, polarized, _FREQ, 0, {"order": 1})
+        rows.append(np.asarray(r).reshape(-1))
+    flat = np.stack(rows)
+    u, s, vh = np.linalg.svd(flat, full_matrices=False)
+    K = int((s / s[0] >= 1e-10).sum())
+    assert len(eb) == K and coefs.shape == (len(beam_list), K)
+    assert K == (7 if polarized else 4)
+    np.testing.assert_allclose(np.linalg.norm(coefs, axis=0), s[:K], rtol=1e-10)
+    V = _flat(eb)
+    Vn = vh[:K]
+    # same subspace: projecting numpy's right-singular vectors onto ours loses nothing
+    assert np.linalg.norm(Vn @ V.conj().T @ V - Vn) < 1e-9
+    # well-separated singular values: vectors agree up to a unit phase
+    for k in range(K):
+        if min(abs(s[k] - s[j]) for j in range(len(s)) if j != k) > 1e-6 * s[0]:
+            assert abs(abs(np.vdot(Vn[k], V[k])) - 1.0) < 1e-9
+    assert relerr(coefs @ V, flat) < 1e-10
+
+
+@pytest.mark.gpu
+def test_basis_simulation_matches_oracle_per_antenna_cpu_pipeline():
+    """compute_beam_basis -> simulate_vis(beam_coefs=...) on the GPU against the ORACLE's CPU pipeline run
+    with the original per-antenna beams (reference tests/test_beam_basis.py:310-431 compares the two
+    CPU paths at atol 1e-5; here the basis grid is the table beams' own grid, so the decomposition is
+    exact and the bar is the NUFFT's)."""
+    from fftvis_b200 import compute_beam_basis, simulate_vis, synth
+    from oracle import pipeline
+    p = _sim_params()
+    nant = len(p["ants"])
+    beams = [synth.synthetic_uvbeam(p["freqs"], naz=72, nza=37, seed=s, perturb=0.3) for s in range(3)]
+    # real-valued beams: the reference's lower-triangle shortcut (swapaxes without conjugation, SURVEY
+    # App. D.5) is exact only for a real basis
+    for b in beams:
+        b.data_array = b.data_array.real.astype(complex)
+    eb, coefs = compute_beam_basis(beams, freq=_FREQ, polarized=True, threshold=1e-12)
+    assert len(eb) == 3
+    beam_idx = np.arange(nant) % 3
+    kw = dict(polarized=True, eps=1e-12, beam_spline_opts={"order": 1})
+    vis_basis = simulate_vis(beam=eb, beam_coefs=coefs[beam_idx, :, np.newaxis], **kw, **p)
+    q = {k: v for k, v in p.items() if k != "fluxes"}
+    cpu = pipeline.simulate_cpu(fluxes=p["fluxes"], beam_list=beams, beam_idx=beam_idx, **kw, **q)
+    direct = pipeline.simulate_direct(fluxes=p["fluxes"], beam_list=beams, beam_idx=beam_idx, polarized=True,
+                                      beam_spline_opts={"order": 1}, **q)
+    assert relerr(cpu, direct) < 1e-11
+    assert relerr(vis_basis, cpu) < 1e-10
+    assert relerr(vis_basis, direct) < 1e-10

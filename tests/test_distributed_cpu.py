@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fftvis_b200.gpu.distributed import gather_slabs, shard_frequencies
+from fftvis_b200.gpu.distributed import SlabGather, gather_slabs, shard_frequencies, shard_inputs
 
 
 def test_shard_frequencies_balanced_and_contiguous():
@@ -60,3 +60,54 @@ def test_gather_slabs_gloo_world2(nf, dst):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def _slab_worker(rank, world, port, nf, nt, dst, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shards = shard_frequencies(nf, world)
+        lo, hi = shards[rank]
+        rng = np.random.default_rng(1)
+        want = rng.normal(size=(nt, nf, 4, 5)) + 1j * rng.normal(size=(nt, nf, 4, 5))
+        if rank == dst:
+            full = torch.zeros((nt, nf, 4, 5), dtype=torch.complex128)
+            sg = SlabGather(shards, full, None, dst=dst)
+        else:
+            local = torch.zeros((nt, hi - lo, 4, 5), dtype=torch.complex128)
+            sg = SlabGather(shards, None, local, dst=dst)
+        for t in range(nt):                      # "compute" slab t, then post its transfer
+            block = torch.as_tensor(want[t, lo:hi])
+            if rank == dst:
+                full[t, lo:hi] = block
+            else:
+                local[t] = block
+            sg.post(t)
+        sg.finish()
+        q.put((rank, bool(np.array_equal(full.numpy(), want)) if rank == dst else True))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nf,nt,dst", [(7, 3, 0), (8, 2, 1), (1, 2, 0)])
+def test_per_time_slab_gather_gloo_world2(nf, nt, dst):
+    """The per-slab point-to-point gather of run_sharded: ragged shards, either destination, a rank
+    with an empty shard."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, nf, nt, dst, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
+
+def test_shard_inputs_cuts_the_frequency_axis():
+    kw = dict(freqs=np.arange(10.0), fluxes=np.arange(30.0).reshape(3, 10), beam_coefs=np.ones((4, 2, 10)), eps=1e-9)
+    s = shard_inputs(kw, 3, 6)
+    assert s["freqs"].tolist() == [3.0, 4.0, 5.0] and s["fluxes"].shape == (3, 3) and s["beam_coefs"].shape == (4, 2, 3)
+    assert s["eps"] == 1e-9 and kw["fluxes"].shape == (3, 10)
+    assert shard_inputs(dict(freqs=np.arange(4.0), fluxes=np.ones((2, 4, 2, 2))), 0, 2)["fluxes"].shape == (2, 2, 2, 2)

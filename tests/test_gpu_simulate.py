@@ -7,7 +7,7 @@ Bar: relative L2 error <= 10 x eps (fp64); fp32 is limited by input rounding (se
 import numpy as np
 import pytest
 
-from gpu_helpers import TIMES, hex_ants, relerr, small_sky
+from gpu_helpers import TIMES, f32_bar, hex_ants, relerr, small_sky
 
 pytestmark = pytest.mark.gpu
 
@@ -42,7 +42,8 @@ def test_cfg1_unpolarized_gaussian(precision, eps, force3):
         assert relerr(got, direct) < 10 * eps
         assert relerr(got, cpu) < 10 * eps
     else:
-        assert relerr(got, direct) < max(3 * relerr(cpu, direct), 1e-5)
+        assert relerr(got, direct) < f32_bar(cpu, direct, eps)
+        assert relerr(got, cpu) < 2 * f32_bar(cpu, direct, eps)
 
 
 @pytest.mark.parametrize("force3", [False, True])
@@ -198,7 +199,10 @@ def test_f32_close_to_f64_and_no_sources_above_horizon():
     beam = AiryBeam(diameter=14.0)
     v64 = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beam, HERA_LOCATION, precision=2)
     v32 = simulate_vis(ants, flux, ra, dec, FREQS, TIMES, beam, HERA_LOCATION, precision=1)
-    assert v32.dtype == np.complex64 and relerr(v32, v64) < 2e-5
+    from oracle import pipeline
+    c32 = pipeline.simulate_cpu(ants, flux, ra, dec, FREQS, TIMES, [beam.to_power()], HERA_LOCATION, precision=1)
+    assert v32.dtype == np.complex64 and relerr(v32, v64) < f32_bar(c32, v64)
+    assert relerr(v32, c32) < 2 * f32_bar(c32, v64)
     # every source below the horizon -> exact zeros
     below_dec = np.full(5, np.deg2rad(80.0))
     out = simulate_vis(ants, flux[:5], ra[:5], below_dec, FREQS, TIMES, beam, HERA_LOCATION, precision=2)
@@ -285,3 +289,43 @@ def test_streamed_result_equals_plain_copy(nchunks):
     assert streamed.shape == (freqs.size, times.size, plain.shape[-1])
     assert np.array_equal(streamed, plain)
     assert np.abs(streamed).max() > 0
+
+
+def test_time_major_output_and_sharded_driver_world1():
+    """``run_plan`` through a permuted (time-major) view, and the frequency-sharded driver
+    (gpu/distributed.py ``simulate_vis_sharded``: per-slab gather + host streaming) on a one-rank NCCL
+    group, must both reproduce ``simulate`` bit for bit.  (world_size 2 runs on CPU over gloo in
+    tests/test_distributed_cpu.py and on 2..8 GPUs in tools/sharded_check.py.)"""
+    import os
+    import socket
+    import torch
+    import torch.distributed as dist
+    from fftvis_b200 import HERA_LOCATION, synth
+    from fftvis_b200.gpu import GPUSimulationEngine
+    from fftvis_b200.gpu.distributed import simulate_vis_sharded
+    ants = hex_ants(4)
+    freqs = np.linspace(100e6, 200e6, 7)
+    times = 2459845.0 + np.arange(3) * 600 / 86400.0
+    ra, dec, flux = small_sky(900, freqs)
+    beam = synth.synthetic_uvbeam(freqs, naz=72, nza=37)
+    kw = dict(ants=ants, freqs=freqs, fluxes=flux, beam_list=[beam], ra=ra, dec=dec, times=times,
+              telescope_loc=HERA_LOCATION, precision=2, eps=1e-12, polarized=True, beam_spline_opts={"order": 1})
+    eng = GPUSimulationEngine(freq_batch=3)
+    ref = eng.simulate(**kw)
+    plan = eng.prepare(**kw)
+    buf = torch.empty((times.size, freqs.size, 4, plan.nbls), dtype=torch.complex128, device="cuda")
+    eng.run_plan(plan, out=buf.permute(1, 0, 2, 3))
+    tm = buf.cpu().numpy().transpose(1, 0, 2, 3).reshape(ref.shape)
+    assert np.array_equal(tm, ref)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        got = simulate_vis_sharded(eng, dst=0, nprocesses=4, **kw)      # CPU-only knobs are accepted
+        assert got.shape == ref.shape and np.array_equal(got, ref)
+        got_all = simulate_vis_sharded(eng, dst=None, **kw)
+        assert np.array_equal(got_all, ref)
+    finally:
+        dist.destroy_process_group()
