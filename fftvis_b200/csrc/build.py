@@ -13,7 +13,12 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 LIB = HERE.parent / "libfftvis_b200.so"
-SOURCES = ["api.cu", "rotate_cut.cu", "weights.cu", "nufft.cu", "type1_fused.cu", "type3.cu"]
+SOURCES = ["api.cu", "rotate_cut.cu", "weights.cu", "nufft.cu", "type1_fused.cu", "type1_small.cu", "type3.cu"]
+# headers each translation unit includes (directly or through nufft_internal.cuh)
+_NUFFT = ["common.cuh", "nufft_internal.cuh", "type1_fused.cuh"]
+DEPS = {"api.cu": ["common.cuh"], "rotate_cut.cu": ["common.cuh"], "weights.cu": ["common.cuh"],
+        "nufft.cu": _NUFFT, "type1_fused.cu": _NUFFT, "type1_small.cu": [*_NUFFT, "type1_small.cuh"],
+        "type3.cu": [*_NUFFT, "type3_tiles.cuh", "type3_fft.cuh"]}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -31,10 +36,10 @@ def _stale(target: Path, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     objdir = HERE / "_obj"
     objdir.mkdir(exist_ok=True)
-    headers = [*sorted(HERE.glob("*.cuh")), ROOT / "include" / "fftvis_b200.h"]
     jobs = []
     for src in SOURCES:
         obj = objdir / (src[:-3] + ".o")
+        headers = [*(HERE / h for h in DEPS[src]), ROOT / "include" / "fftvis_b200.h"]
         if force or _stale(obj, [HERE / src, *headers]):
             cmd = [NVCC, *FLAGS, "-c", str(HERE / src), "-o", str(obj)]
             if verbose:

@@ -118,6 +118,9 @@ extern "C" int fv_plan_destroy(fv_plan* P) {
   if (P->bins) cudaFree(P->bins);
   if (P->grid3) cudaFree(P->grid3);
   if (P->scan_tmp) cudaFree(P->scan_tmp);
+  if (P->small) cudaFree(P->small);
+  if (P->rec) cudaFree(P->rec);
+  for (auto& kv : P->small_scheds) { cudaFree(kv.second.ph_off); cudaFree(kv.second.ph_bins); }
   for (auto& kv : P->smem_ffts) { cudaFree(kv.second.tw); if (kv.second.pos_dev) cudaFree(kv.second.pos_dev); }
   delete P;
   return FV_OK;
@@ -164,7 +167,7 @@ extern "C" int fv_plan_stage_ms(fv_plan* P, int stage, double* ms_host, int64_t*
 
 extern "C" int64_t fv_plan_bytes(fv_plan* P) {
   if (!P) return 0;
-  return (int64_t)(P->grid_bytes + P->grid2_bytes + P->tbuf_bytes + P->prep_bytes + P->bins_bytes + P->grid3_bytes + P->scan_tmp_bytes + P->fft_work_bytes + P->table_bytes);
+  return (int64_t)(P->grid_bytes + P->grid2_bytes + P->tbuf_bytes + P->prep_bytes + P->bins_bytes + P->grid3_bytes + P->scan_tmp_bytes + P->fft_work_bytes + P->table_bytes + P->small_bytes + P->rec_bytes);
 }
 
 extern "C" int fv_nufft2d1(fv_plan* plan, int prec, const void* bx, const void* by, const int32_t* n_dev,
@@ -221,6 +224,7 @@ extern "C" int fv_plan_set_option(fv_plan* P, const char* name, int64_t value) {
   else if (n == "t1_cols") P->t1_cols = (int)value;
   else if (n == "max_grid_bytes") P->max_grid_bytes = (size_t)value;
   else if (n == "t3_tiles") P->t3_tiles = (int)value;
+  else if (n == "t1_small") P->t1_small = (int)value;
   else if (n == "t3_fft") P->t3_fft = (int)value;
   else if (n.rfind("t3_v", 0) == 0 && n.size() == 5 && n[4] >= 'x' && n[4] <= 'z') P->t3_v[n[4] - 'x'] = (int)value;
   else if (n.rfind("t3_thr", 0) == 0 && n.size() == 7 && n[6] >= 'x' && n[6] <= 'z') P->t3_thr[n[6] - 'x'] = (int)value;
@@ -233,7 +237,7 @@ extern "C" int fv_nufft2d1_fused(fv_plan* plan, int prec, const void* bx, const 
                                  fv_modeset* modes, double eps, double upsampfac, const fv_epilogue* epi_host) {
   FV_REQUIRE(plan && bx && by && n_dev && scale_host && W && modes && epi_host && epi_host->out, "null pointer");
   FV_REQUIRE(prec == 1 || prec == 2, "prec must be 1 or 2");
-  FV_REQUIRE(ntr >= 1 && ntr <= 4, "ntr must be 1..4");
+  FV_REQUIRE(ntr >= 1 && ntr <= 64, "ntr must be 1..64");
   FV_REQUIRE(nb >= 0 && (int64_t)nb * ntr <= 65535, "batch too large");
   FV_REQUIRE(upsampfac > 1.0 && eps > 0, "bad eps / upsampfac");
   if (nb == 0 || modes->m1.empty()) return FV_OK;
@@ -308,6 +312,24 @@ extern "C" int fv_basis_contract(int prec, const void* vkl, int nb, int64_t nk, 
   dim3 grid(fv::ceil_div(nk, 256), nb);
   if (prec == 1) fv::basis_contract_kernel<float><<<grid, 256, 0, st>>>((const float2*)vkl, nk, (const float2*)coefs, K, nfreq_total, freq_index0, kk, ll, ant1, ant2, ed);
   else fv::basis_contract_kernel<double><<<grid, 256, 0, st>>>((const double2*)vkl, nk, (const double2*)coefs, K, nfreq_total, freq_index0, kk, ll, ant1, ant2, ed);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+extern "C" int fv_basis_contract_all(int prec, const void* vkl, int nb, int64_t nk, const void* coefs,
+                                     int64_t nant, int K, int64_t nfreq_total, int64_t freq_index0,
+                                     const int32_t* ant1, const int32_t* ant2, const fv_epilogue* epi_host,
+                                     void* stream) {
+  FV_REQUIRE(vkl && coefs && ant1 && ant2 && epi_host && epi_host->out, "null pointer");
+  FV_REQUIRE(prec == 1 || prec == 2, "prec must be 1 or 2");
+  FV_REQUIRE(K >= 1 && K <= 8, "1 <= K <= 8 basis beams");
+  FV_REQUIRE(nant > 0 && nb >= 0 && nb <= 65535, "bad nant / nb");
+  if (nb == 0 || nk == 0) return FV_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  fv::EpiDev ed = fv::make_epi(epi_host);
+  dim3 grid(fv::ceil_div(nk, 256), nb);
+  if (prec == 1) fv::basis_contract_all_kernel<float><<<grid, 256, 0, st>>>((const float2*)vkl, nk, (const float2*)coefs, K, nfreq_total, freq_index0, ant1, ant2, ed);
+  else fv::basis_contract_all_kernel<double><<<grid, 256, 0, st>>>((const double2*)vkl, nk, (const double2*)coefs, K, nfreq_total, freq_index0, ant1, ant2, ed);
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

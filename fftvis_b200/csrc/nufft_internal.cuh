@@ -111,7 +111,8 @@ struct EpiDev {
 template <typename C>
 __device__ __forceinline__ void epilogue_store(const EpiDev& e, int b, int p, int64_t k, C v) {
   if (e.conj_flag && e.conj_flag[k]) v.y = -v.y;
-  const int64_t idx = (int64_t)b * e.sb + (int64_t)e.pmap[p] * e.sp + (e.kmap ? (int64_t)e.kmap[k] : k);
+  // transforms beyond the first four (batched basis pairs) keep the feed map inside their own group of four
+  const int64_t idx = (int64_t)b * e.sb + (int64_t)(e.pmap[p & 3] + (p & ~3)) * e.sp + (e.kmap ? (int64_t)e.kmap[k] : k);
   C* o = (C*)e.out + idx;
   if (e.acc) { C t = *o; t.x += v.x; t.y += v.y; *o = t; } else { *o = v; }
 }
@@ -434,6 +435,47 @@ basis_contract_kernel(const cplx_t<T>* __restrict__ vkl, int64_t nk, const cplx_
     }
 }
 
+// all K (K + 1) / 2 pairs in one pass: vkl (nb, npairs * 4, nk), pair order k <= l row-major
+template <typename T>
+__global__ void __launch_bounds__(256)
+basis_contract_all_kernel(const cplx_t<T>* __restrict__ vkl, int64_t nk, const cplx_t<T>* __restrict__ coefs,
+                          int K, int64_t nfreq_total, int64_t f0, const int32_t* __restrict__ ant1,
+                          const int32_t* __restrict__ ant2, EpiDev e) {
+  using C = cplx_t<T>;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nk) return;
+  const int b = blockIdx.y;
+  const int64_t f = f0 + b;
+  const int a1 = ant1[k], a2 = ant2[k];
+  const int npairs = K * (K + 1) / 2;
+  C acc[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) acc[p] = make_c<T>(T(0), T(0));
+  int q = 0;
+  for (int kk = 0; kk < K; ++kk) {
+    const C c1k = coefs[((int64_t)a1 * K + kk) * nfreq_total + f], c2k = coefs[((int64_t)a2 * K + kk) * nfreq_total + f];
+    for (int ll = kk; ll < K; ++ll, ++q) {
+      const C c1l = coefs[((int64_t)a1 * K + ll) * nfreq_total + f], c2l = coefs[((int64_t)a2 * K + ll) * nfreq_total + f];
+      const C wkl = cmulc(c1k, c2l);      // conj(c[a1,k]) c[a2,l]
+      const C wlk = cmulc(c1l, c2k);      // conj(c[a1,l]) c[a2,k]
+      C v[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) v[p] = vkl[((int64_t)b * npairs * 4 + q * 4 + p) * nk + k];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          // same order of operations as the per-pair kernel: r = wkl v (+ wlk v^T), then accumulate
+          C r = cmul(wkl, v[i * 2 + j]);
+          if (kk != ll) r = cadd(r, cmul(wlk, v[j * 2 + i]));
+          acc[i * 2 + j] = cadd(acc[i * 2 + j], r);
+        }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) epilogue_store(e, b, p, k, acc[p]);
+}
+
 }  // namespace fv
 
 #include "type1_fused.cuh"
@@ -472,6 +514,12 @@ struct fv_plan {
   int t3_v[3] = {0, 0, 0}, t3_thr[3] = {0, 0, 0}; // tuning overrides: vectors per CTA / threads of the x, y, z passes
   int t1_rows = 0;                               // strip height override (0 = automatic)
   int t1_cols = 0;                               // columns per CTA override (0 = automatic)
+  // small-grid type-1 path (type1_small.cuh): sort buffers, records, per-(nf, w) phase schedules
+  void* small = nullptr; size_t small_bytes = 0;
+  void* rec = nullptr; size_t rec_bytes = 0;
+  int t1_small = 1;                              // 0: never; 1: automatic (whole grid in one CTA and >= 4096 source slots); 2: whenever possible
+  struct SmallSched { int nphase = 0; int32_t* ph_off = nullptr; uint16_t* ph_bins = nullptr; };
+  std::map<std::pair<int64_t, int>, SmallSched> small_scheds;
   // geometry of the last type-3 transform: dim, w, nf[3] (spread grid), ng[3] (FFT grid), tiled, own_fft, sub-batch
   int64_t last_geo[12] = {0};
 };
@@ -489,6 +537,12 @@ struct fv_modeset {
 };
 
 namespace fv {
+
+// small-grid type-1 path (type1_small.cu)
+bool t1s_width_built(int w);
+int t1_small_pass1_entry(fv_plan* P, int prec, const int32_t* n_dev, int64_t n_cap, int nb, int ntr, const void* W,
+                         int64_t nf, int w, double beta, const int32_t* ix0, const int32_t* iy0, const void* zx,
+                         const void* zy, const fv_plan::SmemFft* F, const fv_modeset::Tables* tab);
 
 static int ensure(void** p, size_t* have, size_t need) {
   if (*have >= need) return FV_OK;

@@ -146,6 +146,18 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
                                                    R, nstrips, masks ? hm0 : nullptr, masks ? hm1 : nullptr);
     FV_LAUNCH_CHECK();
   }
+  // small grid held whole in one CTA and many sources: bins of sources + register windows (type1_small.cuh)
+  const bool small_ok = whole && R == (int)nf && t1s_width_built(w) && nf % 2 == 0 && (nf / 2) / ((w + 2) / 2) >= 2 &&
+                        (nf / 2) * (nf / 2) < 65536 && (int64_t)nb * n_cap < (1ll << 31) / 40 &&
+                        sizeof(C) * ((size_t)nf * (nf + 1) + nf) + sizeof(int) * (nf + 4096) + 4 * 2 * (8 * 40 * sizeof(T) + 8 * sizeof(C)) + 256 <= smem_max;
+  const bool use_small = small_ok && (P->t1_small == 2 || (P->t1_small == 1 && n_cap >= 4096));
+  if (ntr > 4 && !use_small) {
+    // the strip kernel takes any transform count as well; nothing to do
+  }
+  if (use_small) {
+    rc = t1_small_pass1_entry(P, prec, n_dev, n_cap, nb, ntr, W, nf, w, beta, ix0, iy0, zx, zy, F, tab);
+    if (rc) return rc;
+  }
   T1SpreadArgs<T> a{};
   a.n_dev = n_dev; a.n_cap = n_cap; a.ix0 = ix0; a.iy0 = iy0; a.zx = zx; a.zy = zy;
   a.hm0 = masks ? hm0 : nullptr; a.hm1 = masks ? hm1 : nullptr;
@@ -155,7 +167,7 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   a.beta = (T)beta; a.c = (T)(4.0 / ((double)w * w)); a.halfw = (T)(w / 2.0);
   a.ntr = ntr; a.W = (const C*)W; a.tw = (const C*)F->tw; a.st = F->st;
   a.ncols = ncols; a.col_pos = tab->col_pos; a.Tbuf = (C*)P->tbuf;
-  {
+  if (!use_small) {
     StageScope ts(P, FV_STAGE_SPREAD);
     dim3 grid(ceil_div(nf, R), np == 4 ? nb : nb * ntr);
     const size_t smem = fixed1 + np * sizeof(C) * pitch1 * R;

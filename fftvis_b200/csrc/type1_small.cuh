@@ -1,0 +1,312 @@
+// Type-1 transform on SMALL fine grids (the whole nf x nf grid of one transform fits the shared memory of
+// one CTA: HERA-331-like arrays, nf = 90) with MANY sources per cell -- BASELINE configs[2] and [4]
+// (100k sources, w = 14, four polarisation products, K (K + 1) / 2 basis pairs).
+//
+// The strip kernel of type1_fused.cuh spreads a hit by read-modify-write of its w x w cells in shared
+// memory: 196 cells x 32 B per hit and product, i.e. the shared-memory pipe is the bound and every
+// product re-evaluates the 2 w kernel samples.  Here a hit costs FMAs on REGISTERS instead:
+//
+//   t1s_key_kernel      key (frequency, bin) of every live source: bins are 2 x 2 blocks of footprint
+//                       origins, so all footprints of a bin lie inside one (w + 1) x (w + 1) window
+//   cub radix sort      stable: sources of a bin stay in catalogue order -> deterministic sums
+//   t1s_bounds_kernel   first sorted position of every (frequency, bin)
+//   t1s_records_kernel  kernel samples of every sorted (frequency, source), evaluated ONCE for all products /
+//                       basis pairs and already shifted to window coordinates (zero outside the footprint)
+//   t1s_spread_kernel   one CTA per (frequency, transform).  A warp takes a bin, keeps the bin's window in
+//                       registers (lane = (row group, column), RPL rows each), streams the bin's records:
+//                       acc[r] += (W kx[col]) ky[r], and adds the window to the shared-memory grid once.
+//                       Bins are processed in phases of pairwise disjoint windows (host-built schedule), so
+//                       the adds need no atomics and the order of summation is fixed.  Then the row FFTs
+//                       and the write-out of the needed columns, as in t1_spread_fftx_kernel.
+//
+// Same kernel, width, grid size and deconvolution as the strip path (finufft.nufft2d1, reference
+// cpu/nufft.py:120-175): only the order of the additions differs.
+#pragma once
+
+namespace fv {
+
+template <int WT>
+struct T1Small {
+  static constexpr int S = WT + 1;                       // window side
+  static constexpr int NG = (32 / S) > 0 ? (32 / S) : 1; // row groups per warp
+  static constexpr int RPL = (S + NG - 1) / NG;          // window rows per lane
+  static constexpr int SP = (S + 1) & ~1;                // kx part of a record (padded to even)
+  static constexpr int YP = (NG * RPL + 1) & ~1;         // ky part
+  static constexpr int REC = (SP + YP + 3) & ~3;         // reals per record (16-byte multiples in either precision: bulk copies)
+  static_assert(S <= 32, "kernel width");
+};
+
+template <typename T>
+struct T1SmallArgs {
+  const int32_t* n_dev;
+  int64_t n_cap;
+  int nf, pitch, w, nbd;         // nbd = nf / 2 bins per dimension
+  T beta, c, halfw;
+  int ntr;
+  const cplx_t<T>* W;            // (nb, ntr, n_cap)
+  const int32_t* ix0; const int32_t* iy0; const T* zx; const T* zy;   // t1_prep_kernel, (nb, n_cap)
+  uint32_t* keys; int32_t* vals;          // unsorted (nb * n_cap)
+  const uint32_t* skeys; const int32_t* svals;   // sorted
+  int32_t* off;                  // (nb * nbins + 1) first sorted position of every (frequency, bin)
+  T* rec;                        // (nb * n_cap, REC) records in sorted order
+  int nphase;
+  const int32_t* ph_off;         // (nphase + 1)
+  const uint16_t* ph_bins;       // bins of every phase
+  const cplx_t<T>* tw;
+  FftStages st;
+  int ncols;
+  const int32_t* col_pos;
+  cplx_t<T>* Tbuf;               // (nb, ntr, ncols, nf)
+  int nb;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+t1s_key_kernel(T1SmallArgs<T> a) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.n_cap) return;
+  const int b = blockIdx.y;
+  const int64_t o = (int64_t)b * a.n_cap + s;
+  const int nbins = a.nbd * a.nbd;
+  uint32_t key = (uint32_t)a.nb * (uint32_t)nbins;      // sentinel: sorts behind every live source
+  if (s < *a.n_dev) {
+    const int cx = wrap_idx(a.ix0[o], a.nf), cy = wrap_idx(a.iy0[o], a.nf);
+    key = (uint32_t)b * (uint32_t)nbins + (uint32_t)((cy >> 1) * a.nbd + (cx >> 1));
+  }
+  a.keys[o] = key;
+  a.vals[o] = (int32_t)s;
+}
+
+// off[k] = first sorted position whose key is >= k, k = 0 .. nkeys (nkeys = nb * nbins = the sentinel)
+__global__ void __launch_bounds__(256)
+t1s_bounds_kernel(const uint32_t* __restrict__ skeys, int64_t n, uint32_t nkeys, int32_t* __restrict__ off) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const uint32_t cur = i < n ? min(skeys[i], nkeys) : nkeys;
+  if (i == 0) { for (uint32_t k = 0; k <= cur; ++k) off[k] = 0; return; }
+  const uint32_t prev = min(skeys[i - 1], nkeys);
+  for (uint32_t k = prev + 1; k <= cur; ++k) off[k] = (int32_t)i;
+  if (i == n) for (uint32_t k = cur + 1; k <= nkeys; ++k) off[k] = (int32_t)n;
+}
+
+// one thread per (sorted item, record slot)
+template <typename T, int WT>
+__global__ void __launch_bounds__(256)
+t1s_records_kernel(T1SmallArgs<T> a, int64_t nitems) {
+  using G = T1Small<WT>;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = t / G::REC;
+  if (i >= nitems) return;
+  const int slot = (int)(t - i * G::REC);
+  const int nbins = a.nbd * a.nbd;
+  const uint32_t key = a.skeys[i];
+  if (key >= (uint32_t)a.nb * (uint32_t)nbins) return;   // not a live source
+  const int b = (int)(key / (uint32_t)nbins), bin = (int)(key - (uint32_t)b * nbins);
+  const int by = bin / a.nbd, bx = bin - by * a.nbd;
+  const int64_t o = (int64_t)b * a.n_cap + a.svals[i];
+  T v = T(0);
+  if (slot < G::SP) {
+    const int j = slot - (wrap_idx(a.ix0[o], a.nf) - 2 * bx);      // kernel sample seen by window column `slot`
+    if (slot < G::S && j >= 0 && j < WT) v = es_kernel<T>(a.zx[o] + (T)j, a.beta, a.c, a.halfw);
+  } else {
+    const int r = slot - G::SP;
+    const int j = r - (wrap_idx(a.iy0[o], a.nf) - 2 * by);
+    if (r < G::S && j >= 0 && j < WT) v = es_kernel<T>(a.zy[o] + (T)j, a.beta, a.c, a.halfw);
+  }
+  a.rec[i * G::REC + slot] = v;
+}
+
+// ---- mbarrier + 1-D bulk copy (TMA) helpers: a warp streams the records of its bins through a private
+// double buffer in shared memory; the copy of chunk k + 1 is in flight while chunk k is consumed --------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
+constexpr int T1S_CH = 8;          // records per chunk of the per-warp pipeline
+
+// shared memory of one CTA of t1s_spread_kernel
+template <typename T>
+inline size_t t1s_smem_bytes(int nf, int nphase, int nwarps, int rec_len) {
+  const size_t grid = sizeof(cplx_t<T>) * ((size_t)nf * (nf + 1) + nf);            // strip + twiddles
+  const size_t ints = sizeof(int) * ((size_t)nf + 2 * nphase + 4);                  // colp, done / need counters, item counter
+  const size_t per_warp = 2 * ((size_t)T1S_CH * rec_len * sizeof(T) + T1S_CH * sizeof(cplx_t<T>)) + 16;
+  return ((grid + ints + 15) & ~(size_t)15) + nwarps * per_warp + 16;
+}
+
+template <typename T, int WT>
+__global__ void __launch_bounds__(512)
+t1s_spread_kernel(T1SmallArgs<T> a) {
+  using C = cplx_t<T>;
+  using G = T1Small<WT>;
+  constexpr int CH = T1S_CH;
+  extern __shared__ __align__(16) unsigned char t1s_smem[];
+  const int nf = a.nf, pitch = a.pitch;
+  C* strip = (C*)t1s_smem;                         // nf * pitch
+  C* tw = strip + (size_t)nf * pitch;              // nf
+  int* colp = (int*)(tw + nf);                     // nf
+  int* done = colp + nf;                           // bins of every phase already added to the grid
+  int* need = done + a.nphase;                     // bins of every phase
+  int* next_item = need + a.nphase;                // work counter over the schedule (phase-major)
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  size_t fixed = sizeof(C) * ((size_t)nf * pitch + nf) + sizeof(int) * ((size_t)nf + 2 * a.nphase + 4);
+  fixed = (fixed + 15) & ~(size_t)15;
+  constexpr size_t kRecBytes = (size_t)CH * G::REC * sizeof(T);
+  constexpr size_t kPerWarp = 2 * (kRecBytes + CH * sizeof(C)) + 16;
+  unsigned char* mine = t1s_smem + fixed + (size_t)warp * kPerWarp;
+  T* rbuf = (T*)mine;                              // [2][CH * REC]
+  C* wbuf = (C*)(mine + 2 * kRecBytes);            // [2][CH]
+  const unsigned bar0 = smem_addr(mine + 2 * (kRecBytes + CH * sizeof(C)));   // two mbarriers
+  const int bpi = blockIdx.x;                      // (frequency, transform)
+  const int b = bpi / a.ntr;
+  const int nbins = a.nbd * a.nbd;
+  const int nitems = a.ph_off[a.nphase];
+
+  for (int i = tid; i < nf * pitch; i += nthr) strip[i] = make_c<T>(T(0), T(0));
+  for (int i = tid; i < a.st.tw_len; i += nthr) tw[i] = a.tw[i];
+  for (int i = tid; i < a.ncols; i += nthr) colp[i] = a.col_pos[i];
+  for (int i = tid; i < a.nphase; i += nthr) { done[i] = 0; need[i] = a.ph_off[i + 1] - a.ph_off[i]; }
+  if (tid == 0) *next_item = 0;
+  if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const C* Wp = a.W + (int64_t)bpi * a.n_cap;
+  const int32_t* off = a.off + (int64_t)b * nbins;
+  const int g = lane / G::S, c = lane - g * G::S;  // (row group, window column)
+  const bool lane_on = g < G::NG;
+  const int kx_slot = lane_on ? c : 0;
+  const int ky_slot = G::SP + (lane_on ? g : 0) * G::RPL;
+
+  // fetch cursor (warp-uniform): the item being fetched and the next record of it to request
+  int f_i = 0, f_i1 = 0, f_bin = 0, f_ph = 0;
+  bool exhausted = false;
+  // meta of a chunk: bin, phase, record count, last chunk of its bin
+  struct Chunk { int bin, ph, n, last; };
+  unsigned parity = 0;                              // bit s = parity to wait for on stage s
+  C w_next = make_c<T>(T(0), T(0));
+
+  auto fetch = [&](int stage, Chunk& ck) -> bool {
+    while (!exhausted && f_i >= f_i1) {
+      int j = 0;
+      if (lane == 0) j = atomicAdd(next_item, 1);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      if (j >= nitems) { exhausted = true; break; }
+      f_bin = a.ph_bins[j];
+      // phase of item j: the schedule is phase-major, phases are short runs: walk forward from the last one
+      while (a.ph_off[f_ph + 1] <= j) ++f_ph;
+      f_i = off[f_bin]; f_i1 = off[f_bin + 1];
+      if (f_i >= f_i1 && lane == 0) atomicAdd(&done[f_ph], 1);      // empty bin: nothing to add to the grid
+    }
+    if (exhausted) return false;
+    const int n = min(CH, f_i1 - f_i);
+    ck.bin = f_bin; ck.ph = f_ph; ck.n = n; ck.last = (f_i + n >= f_i1);
+    if (lane == 0) {
+      const unsigned bytes = (unsigned)(n * G::REC * sizeof(T));
+      const unsigned bar = bar0 + 8u * stage;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(smem_addr(rbuf + (size_t)stage * CH * G::REC), a.rec + (int64_t)f_i * G::REC, bytes, bar);
+    }
+    // strengths of the chunk's sources: one gathered load per lane, consumed one chunk later
+    w_next = lane < n ? Wp[a.svals[f_i + lane]] : make_c<T>(T(0), T(0));
+    f_i += n;
+    return true;
+  };
+
+  C acc[G::RPL];
+#pragma unroll
+  for (int r = 0; r < G::RPL; ++r) acc[r] = make_c<T>(T(0), T(0));
+  Chunk cur{}, nxt{};
+  int stage = 0;
+  bool have = fetch(0, nxt);
+  while (have) {
+    cur = nxt;
+    const C w_cur = w_next;
+    __syncwarp();                                   // every lane is done with the other stage's buffers
+    have = fetch(stage ^ 1, nxt);
+    // this chunk: strengths to shared memory (broadcast reads below), records have landed?
+    C* wb = wbuf + stage * CH;
+    if (lane < CH) wb[lane] = w_cur;
+    mbar_wait(bar0 + 8u * stage, (parity >> stage) & 1u);
+    parity ^= 1u << stage;
+    __syncwarp();
+    const T* rb = rbuf + (size_t)stage * CH * G::REC;
+    if (lane_on) {
+#pragma unroll 2
+      for (int r0 = 0; r0 < cur.n; ++r0) {
+        const T* rr = rb + r0 * G::REC;
+        const C wv = wb[r0];
+        const T kx = rr[kx_slot];
+        const C e = make_c<T>(wv.x * kx, wv.y * kx);
+#pragma unroll
+        for (int r = 0; r < G::RPL; ++r) { const T ky = rr[ky_slot + r]; acc[r].x += e.x * ky; acc[r].y += e.y * ky; }
+      }
+    }
+    if (cur.last) {
+      // add the window to the grid once every window of the previous phase is in (windows of one phase are
+      // pairwise disjoint, a lane's cells are its own): no atomics on the grid, fixed order of summation
+      if (cur.ph > 0) {
+        const volatile int* dp = done + (cur.ph - 1);
+        const int want = need[cur.ph - 1];
+        while (*dp < want) __nanosleep(64);
+        __threadfence_block();
+      }
+      if (lane_on) {
+        const int by = cur.bin / a.nbd, bx = cur.bin - by * a.nbd;
+        int col = 2 * bx + c;
+        if (col >= nf) col -= nf;
+#pragma unroll
+        for (int r = 0; r < G::RPL; ++r) {
+          const int wr = g * G::RPL + r;
+          if (wr < G::S) {
+            int row = 2 * by + wr;
+            if (row >= nf) row -= nf;
+            C* cell = strip + row * pitch + col;
+            C v = *cell;
+            v.x += acc[r].x; v.y += acc[r].y;
+            *cell = v;
+          }
+          acc[r] = make_c<T>(T(0), T(0));
+        }
+      }
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) atomicAdd(&done[cur.ph], 1);
+    }
+    stage ^= 1;
+  }
+  __syncthreads();
+
+  smem_fft<T>(strip, nf, pitch, nf, tw, a.st);
+  __syncthreads();
+
+  // needed columns -> T[col][row] (rows contiguous)
+  const int total = a.ncols * nf;
+  const unsigned inv_rows = 0xFFFFFFFFu / (unsigned)nf + 1u;
+  C* Tb = a.Tbuf + (int64_t)bpi * a.ncols * nf;
+#pragma unroll 4
+  for (int i = tid; i < total; i += nthr) {
+    const int ci = (int)__umulhi((unsigned)i, inv_rows);
+    const int rr = i - ci * nf;
+    Tb[(int64_t)ci * nf + rr] = strip[rr * pitch + colp[ci]];
+  }
+}
+
+}  // namespace fv

@@ -232,6 +232,60 @@ coherency_kernel(int mode, const cplx_t<T>* __restrict__ bi, const cplx_t<T>* __
   for (int c = 0; c < 4; ++c) out[c * n + s] = res[c];
 }
 
+// Basis path (cpu_simulate.py:416-468): every basis beam is evaluated ONCE per (source, frequency) and the
+// K (K + 1) / 2 pair products (k <= l) are formed from the K Jones matrices in registers; the strengths of
+// pair q go to transforms 4 q .. 4 q + 3 of the batched NUFFT.
+constexpr int kMaxBasis = 8;
+struct BeamSet { fv_beam b[kMaxBasis]; int K; };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+weights_basis_kernel(int mode, BeamSet bs, const T* __restrict__ az, const T* __restrict__ za,
+                     const int32_t* __restrict__ src_idx, const int32_t* __restrict__ n_dev, int64_t n_cap,
+                     const double* __restrict__ freqs, int64_t f0, const cplx_t<T>* __restrict__ flux,
+                     int64_t nsrc_total, cplx_t<T>* __restrict__ out) {
+  using C = cplx_t<T>;
+  const int n = *n_dev;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int fb = blockIdx.y;
+  const double freq = freqs[f0 + fb];
+  const double a = (double)az[s], z = (double)za[s];
+  C A[kMaxBasis][4];
+#pragma unroll
+  for (int k = 0; k < kMaxBasis; ++k) {
+    if (k < bs.K) {
+      BeamVal v;
+      eval_beam<T>(bs.b[k], a, z, freq, fb, v);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) A[k][c] = make_c<T>((T)v.re[c], (T)v.im[c]);
+    }
+  }
+  const int64_t src = src_idx[s];
+  C Cm[4];
+  if (mode == 1) {
+    Cm[0] = flux[(int64_t)(f0 + fb) * nsrc_total + src];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Cm[c] = flux[((int64_t)(f0 + fb) * 4 + c) * nsrc_total + src];
+  }
+  const int npairs = bs.K * (bs.K + 1) / 2;
+  C* o = out + ((int64_t)fb * npairs * 4) * n_cap + s;
+  int q = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxBasis; ++k)
+#pragma unroll
+    for (int l = k; l < kMaxBasis; ++l) {
+      if (l < bs.K) {
+        C res[4];
+        coherency_product<T>(mode, A[k], A[l], Cm, res);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[(int64_t)(q * 4 + c) * n_cap] = res[c];
+        ++q;
+      }
+    }
+}
+
 static bool same_beam_desc(const fv_beam& a, const fv_beam& b) {
   return a.kind == b.kind && a.is_power == b.is_power && a.diameter == b.diameter &&
          a.table == b.table && a.order == b.order && a.freq_offset == b.freq_offset;
@@ -276,6 +330,43 @@ extern "C" int fv_weights(int prec, int mode, const fv_beam* beam_i_host, const 
         mode, *beam_i_host, *beam_j_host, same, (const double*)az, (const double*)za, src_idx, n_dev,
         n_cap, freqs, freq_index0, (const double2*)flux, nsrc_total, (double2*)out,
         (double2*)out_beam_i);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+extern "C" int fv_weights_basis(int prec, int mode, const fv_beam* beams_host, int K, const void* az, const void* za,
+                                const int32_t* src_idx, const int32_t* n_dev, int64_t n_cap, const double* freqs,
+                                int nf, int64_t freq_index0, const void* flux, int64_t nsrc_total, void* out,
+                                void* stream) {
+  FV_REQUIRE(prec == 1 || prec == 2, "prec must be 1 or 2");
+  FV_REQUIRE(mode == 1 || mode == 2, "the basis path is polarised: mode must be 1 or 2");
+  FV_REQUIRE(beams_host && az && za && src_idx && n_dev && freqs && flux && out, "null pointer");
+  FV_REQUIRE(K >= 1 && K <= fv::kMaxBasis, "1 <= K <= 8 basis beams");
+  fv::BeamSet bs;
+  bs.K = K;
+  for (int k = 0; k < fv::kMaxBasis; ++k) bs.b[k] = beams_host[k < K ? k : 0];
+  for (int k = 0; k < K; ++k) {
+    const fv_beam* b = &bs.b[k];
+    FV_REQUIRE(!b->is_power, "basis beams must be E-field beams");
+    FV_REQUIRE(b->kind >= 0 && b->kind <= 3, "unknown beam kind");
+    if (b->kind == 3) {
+      FV_REQUIRE(b->table && b->nza > 0 && b->naz > 0, "table beam without table");
+      if (!(b->order == 0 || b->order == 1 || b->order == 3)) {
+        fv::set_error("beam interpolation order must be 0, 1 or 3");
+        return FV_ERR_UNSUPPORTED;
+      }
+    }
+  }
+  if (nf == 0 || n_cap == 0) return FV_OK;
+  FV_REQUIRE(nf <= 65535, "at most 65535 frequencies per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(fv::ceil_div(n_cap, 256), nf);
+  if (prec == 1)
+    fv::weights_basis_kernel<float><<<grid, 256, 0, st>>>(mode, bs, (const float*)az, (const float*)za, src_idx, n_dev, n_cap,
+                                                         freqs, freq_index0, (const float2*)flux, nsrc_total, (float2*)out);
+  else
+    fv::weights_basis_kernel<double><<<grid, 256, 0, st>>>(mode, bs, (const double*)az, (const double*)za, src_idx, n_dev, n_cap,
+                                                          freqs, freq_index0, (const double2*)flux, nsrc_total, (double2*)out);
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

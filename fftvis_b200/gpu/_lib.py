@@ -50,6 +50,8 @@ _SIGNATURES = {
     "fv_weights": (c_int, [c_int, c_int, POINTER(fv_beam), POINTER(fv_beam), c_void_p, c_void_p,
                            c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int64,
                            c_void_p, c_void_p, c_void_p]),
+    "fv_weights_basis": (c_int, [c_int, c_int, POINTER(fv_beam), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "fv_coherency": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "fv_plan_create": (c_int, [POINTER(c_void_p), c_void_p]),
     "fv_plan_destroy": (c_int, [c_void_p]),
@@ -79,6 +81,8 @@ _SIGNATURES = {
     "fv_basis_contract": (c_int, [c_int, c_void_p, c_int, c_int64, c_void_p, c_int64, c_int, c_int64,
                                   c_int64, c_int, c_int, c_void_p, c_void_p, POINTER(fv_epilogue),
                                   c_void_p]),
+    "fv_basis_contract_all": (c_int, [c_int, c_void_p, c_int, c_int64, c_void_p, c_int64, c_int, c_int64,
+                                      c_int64, c_void_p, c_void_p, POINTER(fv_epilogue), c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

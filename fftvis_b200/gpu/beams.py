@@ -135,6 +135,21 @@ def launch_weights(prec, mode, beam_i: DeviceBeam, beam_j: DeviceBeam, az, za, s
         "fv_weights")
 
 
+def launch_weights_basis(prec, mode, beams, az, za, src_idx, n_dev, n_cap, freqs_dev, f0, nf, flux, nsrc_total,
+                         out, stream=None):
+    """``fv_weights_basis``: the K basis beams evaluated once per (source, frequency), all K (K + 1) / 2
+    pair products written as the strengths ``out (nf, npairs * 4, n_cap)`` of one batched NUFFT."""
+    st = (stream or torch.cuda.current_stream()).cuda_stream
+    K = len(beams)
+    arr = (_lib.fv_beam * K)()
+    for k, b in enumerate(beams):
+        d = b.descriptor(f0)
+        ctypes.memmove(ctypes.byref(arr[k]), ctypes.byref(d), ctypes.sizeof(d))
+    _lib.check(_lib.lib().fv_weights_basis(
+        prec, mode, arr, K, az.data_ptr(), za.data_ptr(), src_idx.data_ptr(), n_dev.data_ptr(), n_cap,
+        freqs_dev.data_ptr(), nf, f0, flux.data_ptr(), nsrc_total, out.data_ptr(), st), "fv_weights_basis")
+
+
 def evaluate_beam_device(beam, az, za, polarized: bool, freq: float, prec: int = 2, order: int = 1) -> torch.Tensor:
     """One ``fv_weights`` launch: the response of ``beam`` at host directions (az, za) for one
     frequency, left on the device as ``(4, n)`` complex [vector component * 2 + feed] if

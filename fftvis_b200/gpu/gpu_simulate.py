@@ -35,7 +35,7 @@ from ..core import antenna_gridding, catalog, coords
 from ..core import utils as core_utils
 from ..core.simulate import SimulationEngine, default_accuracy_dict
 from . import _lib
-from .beams import DeviceBeam, GPUBeamEvaluator, launch_weights, resolve_interpolation
+from .beams import DeviceBeam, GPUBeamEvaluator, launch_weights, launch_weights_basis, resolve_interpolation
 from .nufft import ModeSet, NufftPlan, default_plan
 
 logger = logging.getLogger(__name__)
@@ -281,7 +281,8 @@ class GPUSimulationEngine(SimulationEngine):
         fb = self.freq_batch
         if fb is None:
             ncols = max((pt.ncols for pt in pairs), default=None) if is_gridded else None
-            fb = self._auto_batch(is_gridded, n_modes, P, precision, eps, float(upsample_factor), n_cap, ncols)
+            npairs = nbeam * (nbeam + 1) // 2 if (beam_coefs is not None and nbeam <= 5) else 1
+            fb = self._auto_batch(is_gridded, n_modes, P * npairs, precision, eps, float(upsample_factor), n_cap, ncols)
         return SimulationPlan(
             precision=precision, polarized=polarized, polarized_sky=pol_sky, nfeeds=2 if polarized else 1,
             eps=float(eps), upsample_factor=float(upsample_factor), use_type1=is_gridded,
@@ -315,7 +316,7 @@ class GPUSimulationEngine(SimulationEngine):
         inside L2 and make the strip CTAs of pass 1 fill whole waves of the 148 SMs."""
         import ctypes
         csize = 8 * precision
-        by_w = max(1, (1 << 30) // max(1, P * n_cap * csize))          # strengths buffer <= 1 GiB
+        by_w = max(1, ((1 << 30) if P <= 4 else (4 << 30)) // max(1, P * n_cap * csize))   # strengths buffer <= 1 GiB (4 GiB: basis pairs)
         if not type1:
             return int(max(1, min(256, by_w, 4)))                      # type-3 grids are large
         w = ctypes.c_int(0); beta = ctypes.c_double(0)
@@ -360,7 +361,12 @@ class GPUSimulationEngine(SimulationEngine):
         w["scratch"] = torch.empty(sb, dtype=torch.uint8, device=dev)
         w["W"] = torch.empty((nb, P, n_cap), dtype=cdt, device=dev)
         if plan.basis is not None:
-            w["vkl"] = torch.empty((nb, 4, plan.nbls), dtype=cdt, device=dev)
+            npairs = plan.basis["K"] * (plan.basis["K"] + 1) // 2
+            if 4 * npairs <= 64:                        # K <= 5: all pairs as one batched transform
+                w["Wb"] = torch.empty((nb, 4 * npairs, n_cap), dtype=cdt, device=dev)
+                w["vkl"] = torch.empty((nb, 4 * npairs, plan.nbls), dtype=cdt, device=dev)
+            else:
+                w["vkl"] = torch.empty((nb, 4, plan.nbls), dtype=cdt, device=dev)
         return w
 
     def run_plan(self, plan: SimulationPlan, out: torch.Tensor | None = None,
@@ -485,8 +491,8 @@ class GPUSimulationEngine(SimulationEngine):
             host_out.data_ptr() + to * slab, nt * slab, out.data_ptr() + to * out.stride(1) * esz,
             out.stride(0) * esz, slab, nfl, 0, copy_st.cuda_stream), "fv_memcpy2d_async")
 
-    def _nufft_batch(self, plan, w, nufft, pt, dim, xlim, scale, nb, epi):
-        W = w["W"][:nb]
+    def _nufft_batch(self, plan, w, nufft, pt, dim, xlim, scale, nb, epi, W=None):
+        W = w["W"][:nb] if W is None else W
         if plan.use_type1 and self.type1_method == "fused":
             nufft.type1_fused(plan.precision, w["xyz"][0], w["xyz"][1], w["n_dev"], scale, W, pt.modes,
                               plan.eps, plan.upsample_factor, epi)
@@ -498,7 +504,38 @@ class GPUSimulationEngine(SimulationEngine):
                         plan.eps, plan.upsample_factor, epi)
 
     def _basis_batch(self, plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st):
-        """K (K + 1) / 2 transforms over all baselines + contraction (cpu_simulate.py:416-468)."""
+        """K (K + 1) / 2 transforms over all baselines + contraction (cpu_simulate.py:416-468): every basis
+        beam is evaluated once per (source, frequency) (``fv_weights_basis``), the pair products are the
+        strengths of ONE batched transform with 4 K (K + 1) / 2 components on the fused type-1 path (the
+        other paths take them four at a time), and one kernel contracts all pairs."""
+        import ctypes
+        L = _lib.lib()
+        b = plan.basis
+        pt = plan.pairs[0]
+        K = b["K"]
+        npairs = K * (K + 1) // 2
+        if "Wb" not in w:
+            return self._basis_batch_pairs(plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st)
+        Wb, vkl = w["Wb"][:nb], w["vkl"]
+        launch_weights_basis(plan.precision, mode, plan.beams[:K], w["az"], w["za"], w["src_idx"], w["n_dev"],
+                             plan.n_cap, plan.freqs_dev, f0, nb, plan.flux, plan.nsrc, Wb, st)
+        if plan.use_type1 and self.type1_method == "fused":
+            epi = _lib.make_epilogue(vkl.data_ptr(), vkl.stride(0), vkl.stride(1), _FEED_SWAP)
+            self._nufft_batch(plan, w, nufft, pt, dim, xlim, scale, nb, epi, W=Wb)
+        else:
+            for q in range(npairs):
+                w["W"][:nb].copy_(Wb[:, 4 * q:4 * q + 4])
+                epi = _lib.make_epilogue(vkl.data_ptr() + 4 * q * vkl.stride(1) * vkl.element_size(),
+                                         vkl.stride(0), vkl.stride(1), _FEED_SWAP)
+                self._nufft_batch(plan, w, nufft, pt, dim, xlim, scale, nb, epi)
+        epo = _lib.make_epilogue(obase, sb_, sp_, (0, 1, 2, 3), accumulate=True)
+        _lib.check(L.fv_basis_contract_all(
+            plan.precision, vkl.data_ptr(), nb, plan.nbls, b["coefs"].data_ptr(), b["nant"], K,
+            plan.freqs_host.size, f0, b["ant1"].data_ptr(), b["ant2"].data_ptr(),
+            ctypes.byref(epo), st.cuda_stream), "fv_basis_contract_all")
+
+    def _basis_batch_pairs(self, plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st):
+        """More than five basis beams (over 64 batched components): one transform per pair."""
         import ctypes
         L = _lib.lib()
         b = plan.basis

@@ -125,6 +125,14 @@ int fv_weights(int prec, int mode, const fv_beam* beam_i_host, const fv_beam* be
                int64_t freq_index0,
                const void* flux, int64_t nsrc_total, void* out, void* out_beam_i, void* stream);
 
+/* Basis path (_compute_basis_visibilities, cpu_simulate.py:303-470, weights part :416-450): the K basis
+ * beams (beams_host[0..K), E-field, K <= 8) are evaluated once per (source, frequency) and all
+ * K (K + 1) / 2 pair products (k <= l, row-major) are written as the strengths of one batched NUFFT:
+ * out (nf, npairs * 4, n_cap) cplx, pair q at transforms 4 q .. 4 q + 3.  mode 1 or 2 as in fv_weights. */
+int fv_weights_basis(int prec, int mode, const fv_beam* beams_host, int K, const void* az, const void* za,
+                     const int32_t* src_idx, const int32_t* n_dev, int64_t n_cap, const double* freqs, int nf,
+                     int64_t freq_index0, const void* flux, int64_t nsrc_total, void* out, void* stream);
+
 /* stand-alone apparent-coherency products on caller-supplied beam values: the four methods of
  * CPUBeamEvaluator (cpu/beams.py:129-246).  mode 1: A_i^H diag(F) A_j; mode 4: A_i^H C A_j;
  * mode 2: as 4 with both beams flipped along the vector axis (cpu_simulate.py:146-147,153).
@@ -237,6 +245,14 @@ int fv_basis_contract(int prec, const void* vkl, int nb, int64_t nk, const void*
                       int64_t nant, int K, int64_t nfreq_total, int64_t freq_index0, int kk, int ll,
                       const int32_t* ant1, const int32_t* ant2, const fv_epilogue* epi_host,
                       void* stream);
+
+/* The same contraction over ALL K (K + 1) / 2 pairs in one pass: vkl (nb, npairs * 4, nk), pair q =
+ * (kk, ll), kk <= ll in row-major order, at transforms 4 q .. 4 q + 3 -- the layout one batched NUFFT
+ * call with ntr = 4 npairs writes (cpu_simulate.py:416-468, the double loop over k <= l). */
+int fv_basis_contract_all(int prec, const void* vkl, int nb, int64_t nk, const void* coefs,
+                          int64_t nant, int K, int64_t nfreq_total, int64_t freq_index0,
+                          const int32_t* ant1, const int32_t* ant2, const fv_epilogue* epi_host,
+                          void* stream);
 
 #ifdef __cplusplus
 }

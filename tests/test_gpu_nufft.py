@@ -333,3 +333,42 @@ def test_gpu_direct_sum_matches_oracle():
     for b, s in enumerate((1.0, 0.5)):
         want = nc.direct_sum(x[0], x[1], x[2], W[b], u[0] * s, u[1] * s, u[2] * s)
         assert relerr(got[b], want) < 1e-13
+
+
+@pytest.mark.parametrize("prec,eps", [(2, 1e-13), (2, 1e-10), (2, 1e-6), (1, 6e-8), (1, 1e-6)])
+@pytest.mark.parametrize("n_modes,ntr,upsamp", [(41, 4, 2.0), (41, 9, 2.0), (33, 1, 2.0), (61, 2, 1.25)])
+def test_type1_small_grid_register_window_path(prec, eps, n_modes, ntr, upsamp):
+    """Small-grid path (type1_small.cuh: sources bin-sorted into 2 x 2 origin bins, the bin's window in
+    registers, phases of disjoint windows): forced on, against the direct sum, the strip kernel and itself
+    (bit-reproducible), with more than four transforms per frequency (batched basis pairs) and grid sizes
+    whose bins do not divide evenly into classes."""
+    from fftvis_b200.gpu import gpu_nufft2d_type1
+    from fftvis_b200.gpu.nufft import default_plan
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(n_modes + ntr)
+    n, nk = 20000, 300
+    rd, cd = _types(prec)
+    x = rng.uniform(-60, 60, n).astype(rd)
+    y = rng.uniform(-60, 60, n).astype(rd)
+    c = (rng.normal(size=(ntr, n)) + 1j * rng.normal(size=(ntr, n))).astype(cd)
+    h = n_modes // 2
+    idx = rng.integers(-h, h + 1, size=(2, nk))
+    idx[:, :4] = [[-h, h, 0, h], [h, -h, 0, h]]
+    plan = default_plan()
+    outs = []
+    try:
+        for small in (2, 2, 0):
+            plan.set_option("t1_small", small)
+            outs.append(gpu_nufft2d_type1(x, y, c, n_modes, idx, eps, upsample_factor=upsamp, method="fused"))
+    finally:
+        plan.set_option("t1_small", 1)
+    assert np.array_equal(outs[0], outs[1])
+    want = nc.direct_sum(x, y, None, c, idx[0], idx[1], None)
+    floor = 1e-9 if upsamp == 1.25 else 0.0
+    if prec == 2:
+        assert relerr(outs[0], want) < max(10 * eps, floor)
+        assert relerr(outs[0], outs[2]) < max(10 * eps, floor)
+    else:
+        cpu = nc.cpu_nufft2d_type1(x, y, c, n_modes, idx, eps, upsamp)
+        assert relerr(outs[0], want) < f32_bar(cpu, want, eps)
+        assert relerr(outs[0], cpu) < 2 * f32_bar(cpu, want, eps)
