@@ -147,9 +147,14 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
     FV_LAUNCH_CHECK();
   }
   // small grid held whole in one CTA and many sources: bins of sources + register windows (type1_small.cuh)
-  const bool small_ok = whole && R == (int)nf && t1s_width_built(w) && nf % 2 == 0 && (nf / 2) / ((w + 2) / 2) >= 2 &&
-                        (nf / 2) * (nf / 2) < 65536 && (int64_t)nb * n_cap < (1ll << 31) / 40 &&
-                        sizeof(C) * ((size_t)nf * (nf + 1) + nf) + sizeof(int) * (nf + 4096) + 4 * 2 * (8 * 40 * sizeof(T) + 8 * sizeof(C)) + 256 <= smem_max;
+  bool small_ok = whole && R == (int)nf && t1s_width_built(w) && (int64_t)nb * n_cap < (1ll << 31) / 40;
+  if (small_ok) {
+    const int B = 4 * ((w + 4) / 4) - w + 1 < 2 ? 0 : [&] { for (int q = std::min(4 * ((w + 4) / 4) - w + 1, 6); q >= 2; --q) if (nf % q == 0) return q; return 0; }();
+    const int64_t nbd = B ? nf / B : 0;
+    small_ok = B >= 2 && nbd / ((w + 2 * B - 2) / B) >= 2 && nbd * nbd < 65536 &&
+               sizeof(C) * ((size_t)nf * (nf + 1) + nf) + sizeof(int) * (nf + 4096 + nbd * nbd) + 2 * nbd * nbd +
+                       4 * 2 * (8 * 32 * sizeof(T) + 8 * sizeof(C)) + 256 <= smem_max;
+  }
   const bool use_small = small_ok && (P->t1_small == 2 || (P->t1_small == 1 && n_cap >= 4096));
   if (ntr > 4 && !use_small) {
     // the strip kernel takes any transform count as well; nothing to do

@@ -7,7 +7,7 @@
 namespace fv {
 
 // ---- small-grid path (type1_small.cuh) ------------------------------------------------------------
-bool t1s_width_built(int w) { return w == 7 || w == 9 || w == 11 || w == 12 || w == 13 || w == 14 || w == 16; }
+bool t1s_width_built(int w) { return w == 7 || w == 9 || w == 11 || w == 12 || w == 13 || w == 14; }
 
 #define FV_DISPATCH_WS(WV, CALL)                        \
   switch (WV) {                                         \
@@ -16,19 +16,19 @@ bool t1s_width_built(int w) { return w == 7 || w == 9 || w == 11 || w == 12 || w
     case 11: { constexpr int WT = 11; CALL; } break;    \
     case 12: { constexpr int WT = 12; CALL; } break;    \
     case 13: { constexpr int WT = 13; CALL; } break;    \
-    case 14: { constexpr int WT = 14; CALL; } break;    \
-    default: { constexpr int WT = 16; CALL; } break;    \
+    default: { constexpr int WT = 14; CALL; } break;    \
   }
 
-// Phases of bins with pairwise disjoint (w + 1)-cell windows on the periodic grid.  Per dimension the
-// nbd = nf / 2 bins are split into classes whose members are >= D = ceil((w + 1) / 2) bins apart
+// Phases of bins with pairwise disjoint (w + B - 1)-cell windows on the periodic grid.  Per dimension the
+// nbd = nf / B bins are split into classes whose members are >= D = ceil((w + B - 1) / B) bins apart
 // cyclically: m = nbd / D members per class at stride nbd / m, plus one single-bin class for each of the
 // nbd % m left-over bins; a phase is the product of an x class and a y class.
 static int get_small_sched(fv_plan* P, int64_t nf, int w, fv_plan::SmallSched** out) {
   auto key = std::make_pair(nf, w);
   auto it = P->small_scheds.find(key);
   if (it != P->small_scheds.end()) { *out = &it->second; return FV_OK; }
-  const int nbd = (int)(nf / 2), D = (w + 2) / 2;
+  const int B = t1s_bin_size(nf, w);
+  const int nbd = (int)(nf / B), D = (w + B - 1 + B - 1) / B;
   const int m = nbd / D, stride = nbd / m, rem = nbd - m * stride;
   std::vector<std::vector<int>> cls;
   for (int c = 0; c < stride; ++c) {
@@ -60,11 +60,11 @@ template <typename T, int WT>
 static int launch_t1s(fv_plan* P, T1SmallArgs<T>& a, int nb, int ntr, int64_t nitems) {
   // as many warps (<= 16) as the per-warp record buffers leave room for beside the grid
   int nwarps = 16;
-  while (nwarps > 4 && t1s_smem_bytes<T>(a.nf, a.nphase, nwarps, T1Small<WT>::REC) > 226 * 1024) nwarps -= 4;
-  const size_t smem = t1s_smem_bytes<T>(a.nf, a.nphase, nwarps, T1Small<WT>::REC);
+  while (nwarps > 4 && t1s_smem_bytes<T>(a.nf, a.nbd, a.nphase, nwarps, T1Small<WT>::REC) > 226 * 1024) nwarps -= 4;
+  const size_t smem = t1s_smem_bytes<T>(a.nf, a.nbd, a.nphase, nwarps, T1Small<WT>::REC);
   if (smem > 226 * 1024) { set_error("small-grid type-1 path: grid does not fit shared memory"); return FV_ERR_UNSUPPORTED; }
   {
-    const int64_t nt = nitems * T1Small<WT>::REC;
+    const int64_t nt = nitems * 2;
     t1s_records_kernel<T, WT><<<(unsigned)((nt + 255) / 256), 256, 0, P->stream>>>(a, nitems);
     FV_LAUNCH_CHECK();
   }
@@ -85,11 +85,12 @@ static int t1_small_pass1(fv_plan* P, const int32_t* n_dev, int64_t n_cap, int n
   int rc = get_small_sched(P, nf, w, &sc);
   if (rc) return rc;
   const int64_t nitems = (int64_t)nb * n_cap;
-  const int nbd = (int)(nf / 2), nbins = nbd * nbd;
+  const int B = t1s_bin_size(nf, w);
+  const int nbd = (int)(nf / B), nbins = nbd * nbd;
   const int64_t nkeys = (int64_t)nb * nbins;
   int end_bit = 1;
   while ((1ll << end_bit) <= nkeys) ++end_bit;
-  const int rec_len = 2 * (w + 4);                       // >= T1Small<w>::REC for every built width
+  const int rec_len = 8 * ((w + 4) / 4);                 // T1Small<w>::REC
   rc = ensure(&P->rec, &P->rec_bytes, sizeof(T) * (size_t)nitems * rec_len);
   if (rc) return rc;
   const size_t off_bytes = sizeof(int32_t) * ((size_t)nkeys + 2);
@@ -103,7 +104,7 @@ static int t1_small_pass1(fv_plan* P, const int32_t* n_dev, int64_t n_cap, int n
   a.skeys = skeys; a.svals = svals;
   a.off = (int32_t*)(svals + nitems);
   a.rec = (T*)P->rec;
-  a.n_dev = n_dev; a.n_cap = n_cap; a.nf = (int)nf; a.pitch = (int)nf + 1; a.w = w; a.nbd = nbd;
+  a.n_dev = n_dev; a.n_cap = n_cap; a.nf = (int)nf; a.pitch = (int)nf + 1; a.w = w; a.nbd = nbd; a.B = B;
   a.beta = (T)beta; a.c = (T)(4.0 / ((double)w * w)); a.halfw = (T)(w / 2.0);
   a.ntr = ntr; a.W = (const C*)W; a.ix0 = ix0; a.iy0 = iy0; a.zx = zx; a.zy = zy;
   a.nphase = sc->nphase; a.ph_off = sc->ph_off; a.ph_bins = sc->ph_bins;
