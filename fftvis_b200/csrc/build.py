@@ -13,11 +13,12 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 LIB = HERE.parent / "libfftvis_b200.so"
-SOURCES = ["api.cu", "rotate_cut.cu", "weights.cu", "nufft.cu", "type1_fused.cu", "type1_small.cu", "type3.cu"]
+SOURCES = ["api.cu", "rotate_cut.cu", "weights.cu", "nufft.cu", "type1_fused.cu", "type1_small.cu", "type1_xdirect.cu", "type3.cu"]
 # headers each translation unit includes (directly or through nufft_internal.cuh)
 _NUFFT = ["common.cuh", "nufft_internal.cuh", "type1_fused.cuh"]
 DEPS = {"api.cu": ["common.cuh"], "rotate_cut.cu": ["common.cuh"], "weights.cu": ["common.cuh"],
         "nufft.cu": _NUFFT, "type1_fused.cu": _NUFFT, "type1_small.cu": [*_NUFFT, "type1_small.cuh"],
+        "type1_xdirect.cu": [*_NUFFT, "type1_xdirect.cuh"],
         "type3.cu": [*_NUFFT, "type3_tiles.cuh", "type3_fft.cuh"]}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -206,6 +206,7 @@ extern "C" int fv_modeset_destroy(fv_modeset* M) {
   for (auto& kv : M->tables) {
     cudaFree(kv.second.col_pos); cudaFree(kv.second.col_off); cudaFree(kv.second.s_k);
     cudaFree(kv.second.s_pos); cudaFree(kv.second.s_scale);
+    cudaFree(kv.second.col_k); cudaFree(kv.second.s_scale_y);
   }
   delete M;
   return FV_OK;
@@ -225,6 +226,7 @@ extern "C" int fv_plan_set_option(fv_plan* P, const char* name, int64_t value) {
   else if (n == "max_grid_bytes") P->max_grid_bytes = (size_t)value;
   else if (n == "t3_tiles") P->t3_tiles = (int)value;
   else if (n == "t1_small") P->t1_small = (int)value;
+  else if (n == "t1_xdirect") P->t1_xdirect = (int)value;
   else if (n == "t3_fft") P->t3_fft = (int)value;
   else if (n.rfind("t3_v", 0) == 0 && n.size() == 5 && n[4] >= 'x' && n[4] <= 'z') P->t3_v[n[4] - 'x'] = (int)value;
   else if (n.rfind("t3_thr", 0) == 0 && n.size() == 7 && n[6] >= 'x' && n[6] <= 'z') P->t3_thr[n[6] - 'x'] = (int)value;

@@ -517,6 +517,7 @@ struct fv_plan {
   // small-grid type-1 path (type1_small.cuh): sort buffers, records, per-(nf, w) phase schedules
   void* small = nullptr; size_t small_bytes = 0;
   void* rec = nullptr; size_t rec_bytes = 0;
+  int t1_xdirect = 1;                            // 0: never; 1: single precision, grid of several strips (type1_xdirect.cuh)
   int t1_small = 1;                              // 0: never; 1: automatic (whole grid in one CTA and >= 4096 source slots); 2: whenever possible
   struct SmallSched { int nphase = 0; int32_t* ph_off = nullptr; uint16_t* ph_bins = nullptr; };
   std::map<std::pair<int64_t, int>, SmallSched> small_scheds;
@@ -532,11 +533,20 @@ struct fv_modeset {
     int ncols = 0;
     int32_t* col_pos = nullptr; int32_t* col_off = nullptr; int32_t* s_k = nullptr; int32_t* s_pos = nullptr;
     void* s_scale = nullptr;
+    int32_t* col_k = nullptr;      // signed first mode number of every column (x-direct pass 1)
+    void* s_scale_y = nullptr;     // 1 / phihat(m2) only: the x-direct pass 1 has no kernel to divide out along x
   };
   std::map<std::tuple<int, int64_t, int, double>, Tables> tables;   // (prec, nf, w, beta)
 };
 
 namespace fv {
+
+// x-direct pass 1 (type1_xdirect.cu)
+bool t1_xdirect_built(int w);
+int t1_xdirect_rows();
+int t1_xdirect_pass1_entry(fv_plan* P, const int32_t* n_dev, int64_t n_cap, int nb, int ntr, const void* W, int64_t nf,
+                           int w, double beta, const int32_t* iy0, const float* zy, const uint32_t* xt,
+                           const uint32_t* hm0, const uint32_t* hm1, const fv_modeset::Tables* tab);
 
 // small-grid type-1 path (type1_small.cu)
 bool t1s_width_built(int w);

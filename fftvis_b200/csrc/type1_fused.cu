@@ -17,18 +17,20 @@ static int get_modeset_tables(fv_plan* P, fv_modeset* M, int prec, int64_t nf, i
   std::vector<int32_t> order(nk);
   for (int64_t k = 0; k < nk; ++k) order[k] = (int32_t)k;
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return M->m1[a] < M->m1[b]; });
-  std::vector<int32_t> col_pos, col_off, s_k(nk), s_pos(nk);
-  std::vector<T> s_scale(nk);
+  std::vector<int32_t> col_pos, col_off, col_k, s_k(nk), s_pos(nk);
+  std::vector<T> s_scale(nk), s_scale_y(nk);
   for (int64_t i = 0; i < nk; ++i) {
     const int32_t k = order[i];
     const int a1 = M->m1[k], a2 = M->m2[k];
     if (i == 0 || a1 != M->m1[order[i - 1]]) {
       col_off.push_back((int32_t)i);
       col_pos.push_back(F.pos[a1 < 0 ? a1 + nf : a1]);
+      col_k.push_back(a1);
     }
     s_k[i] = k;
     s_pos[i] = F.pos[a2 < 0 ? a2 + nf : a2];
     s_scale[i] = (T)(1.0 / (ph[abs(a1)] * ph[abs(a2)]));
+    s_scale_y[i] = (T)(1.0 / ph[abs(a2)]);
     (void)half;
   }
   col_off.push_back((int32_t)nk);
@@ -45,6 +47,8 @@ static int get_modeset_tables(fv_plan* P, fv_modeset* M, int prec, int64_t nf, i
   if ((rc = up(s_k.data(), s_k.size() * 4, (void**)&t.s_k))) return rc;
   if ((rc = up(s_pos.data(), s_pos.size() * 4, (void**)&t.s_pos))) return rc;
   if ((rc = up(s_scale.data(), s_scale.size() * sizeof(T), &t.s_scale))) return rc;
+  if ((rc = up(col_k.data(), col_k.size() * 4, (void**)&t.col_k))) return rc;
+  if ((rc = up(s_scale_y.data(), s_scale_y.size() * sizeof(T), &t.s_scale_y))) return rc;
   FV_CUDA(cudaStreamSynchronize(P->stream));
   auto res = M->tables.emplace(key, t);
   *out = &res.first->second;
@@ -127,11 +131,15 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   size_t fixed1 = t1_spread_fixed_smem<T>((int)nf, wmax, threads, np);
   while (R > 1 && fixed1 + np * row_bytes * R > smem_max) --R;
   if (fixed1 + np * row_bytes * R > smem_max) { set_error("fine-grid row does not fit shared memory: use the cuFFT type-1 path"); return FV_ERR_UNSUPPORTED; }
+  // x-direct pass 1 (type1_xdirect.cuh): single precision, a grid of several strips
+  const bool use_xd = sizeof(T) == 4 && P->t1_xdirect && !whole && P->t1_rows == 0 && t1_xdirect_built(w) &&
+                      nf >= 2 * (t1_xdirect_rows() + w);
+  if (use_xd) R = t1_xdirect_rows();
   // fold every (frequency, source) point once
   const size_t per = (size_t)nb * n_cap;
   const int nstrips = ceil_div(nf, R);
   const bool masks = nstrips > 1 && nstrips <= 64;           // strip membership of every source as two 32-bit masks
-  rc = ensure(&P->prep, &P->prep_bytes, per * (4 * sizeof(int32_t) + 2 * sizeof(T)));
+  rc = ensure(&P->prep, &P->prep_bytes, per * (5 * sizeof(int32_t) + 2 * sizeof(T)));
   if (rc) return rc;
   int32_t* ix0 = (int32_t*)P->prep;
   int32_t* iy0 = ix0 + per;
@@ -139,15 +147,16 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   uint32_t* hm1 = hm0 + per;
   T* zx = (T*)(hm1 + per);
   T* zy = zx + per;
+  uint32_t* xt = (uint32_t*)(zy + per);
   {
     StageScope ts(P, FV_STAGE_ZERO);
     dim3 grid(ceil_div(n_cap, 256), nb);
     t1_prep_kernel<T><<<grid, 256, 0, P->stream>>>((const T*)bx, (const T*)by, n_dev, n_cap, P->bp_dev, (int)nf, w, ix0, iy0, zx, zy,
-                                                   R, nstrips, masks ? hm0 : nullptr, masks ? hm1 : nullptr);
+                                                   R, nstrips, masks ? hm0 : nullptr, masks ? hm1 : nullptr, use_xd ? xt : nullptr);
     FV_LAUNCH_CHECK();
   }
   // small grid held whole in one CTA and many sources: bins of sources + register windows (type1_small.cuh)
-  bool small_ok = whole && R == (int)nf && t1s_width_built(w) && (int64_t)nb * n_cap < (1ll << 31) / 40;
+  bool small_ok = !use_xd && whole && R == (int)nf && t1s_width_built(w) && (int64_t)nb * n_cap < (1ll << 31) / 40;
   if (small_ok) {
     const int B = 4 * ((w + 4) / 4) - w + 1 < 2 ? 0 : [&] { for (int q = std::min(4 * ((w + 4) / 4) - w + 1, 6); q >= 2; --q) if (nf % q == 0) return q; return 0; }();
     const int64_t nbd = B ? nf / B : 0;
@@ -158,6 +167,12 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   const bool use_small = small_ok && (P->t1_small == 2 || (P->t1_small == 1 && n_cap >= 4096));
   if (ntr > 4 && !use_small) {
     // the strip kernel takes any transform count as well; nothing to do
+  }
+  if (use_xd) {
+    StageScope ts(P, FV_STAGE_SPREAD);
+    rc = t1_xdirect_pass1_entry(P, n_dev, n_cap, nb, ntr, W, nf, w, beta, iy0, (const float*)zy, xt,
+                                masks ? hm0 : nullptr, masks ? hm1 : nullptr, tab);
+    if (rc) return rc;
   }
   if (use_small) {
     rc = t1_small_pass1_entry(P, prec, n_dev, n_cap, nb, ntr, W, nf, w, beta, ix0, iy0, zx, zy, F, tab);
@@ -172,7 +187,7 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   a.beta = (T)beta; a.c = (T)(4.0 / ((double)w * w)); a.halfw = (T)(w / 2.0);
   a.ntr = ntr; a.W = (const C*)W; a.tw = (const C*)F->tw; a.st = F->st;
   a.ncols = ncols; a.col_pos = tab->col_pos; a.Tbuf = (C*)P->tbuf;
-  if (!use_small) {
+  if (!use_small && !use_xd) {
     StageScope ts(P, FV_STAGE_SPREAD);
     dim3 grid(ceil_div(nf, R), np == 4 ? nb : nb * ntr);
     const size_t smem = fixed1 + np * sizeof(C) * pitch1 * R;
@@ -207,7 +222,7 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   T1GatherArgs<T> g{};
   g.Tbuf = (const C*)P->tbuf; g.nf = (int)nf; g.pitch = pitch; g.ncols = ncols; g.cols_per_cta = cpc; g.ntr = ntr;
   g.tw = (const C*)F->tw; g.st = F->st; g.col_off = tab->col_off; g.s_k = tab->s_k; g.s_pos = tab->s_pos;
-  g.s_scale = (const T*)tab->s_scale; g.epi = make_epi(epi);
+  g.s_scale = (const T*)(use_xd ? tab->s_scale_y : tab->s_scale); g.epi = make_epi(epi);
   {
     StageScope ts(P, FV_STAGE_GATHER);
     auto kern = t1_ffty_gather_kernel<T>;

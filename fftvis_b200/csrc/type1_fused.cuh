@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256)
 t1_prep_kernel(const T* __restrict__ bx, const T* __restrict__ by, const int32_t* __restrict__ n_dev,
                int64_t n_cap, const BatchParams* __restrict__ bp, int nf, int w, int32_t* __restrict__ ix0,
                int32_t* __restrict__ iy0, T* __restrict__ zx, T* __restrict__ zy, int R, int nstrips,
-               uint32_t* __restrict__ hm0, uint32_t* __restrict__ hm1) {
+               uint32_t* __restrict__ hm0, uint32_t* __restrict__ hm1, uint32_t* __restrict__ xt) {
   const int n = *n_dev;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
@@ -282,6 +282,12 @@ t1_prep_kernel(const T* __restrict__ bx, const T* __restrict__ by, const int32_t
   const double gy = fold_grid((double)(by[s] * smul), nf), giy = ceil(gy - hw);
   ix0[o] = (int)gix; zx[o] = (T)(gix - gx);
   iy0[o] = (int)giy; zy[o] = (T)(giy - gy);
+  if (xt) {
+    // x itself as a fraction of a turn in 32-bit fixed point (x = 0 -> 0): k * xt wraps mod one turn exactly
+    double r = (double)(bx[s] * smul) * 0.15915494309189533577;
+    r -= floor(r);
+    xt[o] = (uint32_t)(unsigned long long)(r * 4294967296.0 + 0.5);
+  }
   if (hm0) {
     // which strips (of R rows; at most 64) the w footprint rows touch, as two 32-bit masks: the strip
     // CTAs of pass 1 then test one bit per source instead of redoing the row arithmetic

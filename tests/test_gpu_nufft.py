@@ -372,3 +372,42 @@ def test_type1_small_grid_register_window_path(prec, eps, n_modes, ntr, upsamp):
         cpu = nc.cpu_nufft2d_type1(x, y, c, n_modes, idx, eps, upsamp)
         assert relerr(outs[0], want) < f32_bar(cpu, want, eps)
         assert relerr(outs[0], cpu) < 2 * f32_bar(cpu, want, eps)
+
+
+@pytest.mark.parametrize("eps", [6e-8, 1e-5, 1e-3, 1e-1])
+@pytest.mark.parametrize("n_modes,ntr,nk", [(465, 1, 700), (251, 4, 300), (999, 1, 900), (131, 2, 200)])
+def test_type1_xdirect_pass1(eps, n_modes, ntr, nk):
+    """Single-precision pass 1 without an x grid (type1_xdirect.cuh) against the direct sum, the CPU
+    restatement and the strip kernel it replaces: kernel widths from 2 to 9, more than 256 needed columns
+    (two column groups), more than 64 strips (nf = 2000: row compare instead of strip masks), strips that do
+    not divide nf (nf = 270), sources whose footprint wraps around both grid edges."""
+    from fftvis_b200.gpu import gpu_nufft2d_type1
+    from fftvis_b200.gpu.nufft import default_plan
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(n_modes + ntr)
+    n = 4000
+    x = rng.uniform(-60, 60, n).astype(np.float32)
+    y = rng.uniform(-60, 60, n).astype(np.float32)
+    # footprints across the periodic edge of the fine grid in x and y
+    x[:8] = np.float32(np.pi) * np.array([1, -1, 1, -1, 3, -3, 1, 1], np.float32) + np.float32(1e-3) * np.arange(-4, 4, dtype=np.float32)
+    y[4:12] = np.float32(np.pi) * np.array([1, -1, 1, -1, 3, -3, 5, -5], np.float32) + np.float32(2e-3) * np.arange(-4, 4, dtype=np.float32)
+    c = (rng.normal(size=(ntr, n)) + 1j * rng.normal(size=(ntr, n))).astype(np.complex64)
+    h = n_modes // 2
+    idx = rng.integers(-h, h + 1, size=(2, nk))
+    idx[:, :4] = [[-h, h, 0, h], [h, -h, 0, h]]
+    plan = default_plan()
+    got = gpu_nufft2d_type1(x, y, c, n_modes, idx, eps, method="fused")
+    plan.set_option("t1_xdirect", 0)
+    try:
+        old = gpu_nufft2d_type1(x, y, c, n_modes, idx, eps, method="fused")
+    finally:
+        plan.set_option("t1_xdirect", 1)
+    want = nc.direct_sum(x, y, None, c, idx[0], idx[1], None)
+    cpu = nc.cpu_nufft2d_type1(x, y, c, n_modes, idx, eps, 2.0)
+    bar = f32_bar(cpu, want, eps)
+    assert relerr(got, want) < bar
+    assert relerr(got, cpu) < 2 * bar
+    assert relerr(got, old) < 2 * bar
+    assert not np.array_equal(got, old)          # the two pass-1 kernels really are different code paths
+    again = gpu_nufft2d_type1(x, y, c, n_modes, idx, eps, method="fused")
+    assert np.array_equal(got, again)            # fixed summation order: bitwise reproducible
