@@ -544,9 +544,8 @@ namespace fv {
 // x-direct pass 1 (type1_xdirect.cu)
 bool t1_xdirect_built(int w);
 int t1_xdirect_rows();
-int t1_xdirect_pass1_entry(fv_plan* P, const int32_t* n_dev, int64_t n_cap, int nb, int ntr, const void* W, int64_t nf,
-                           int w, double beta, const int32_t* iy0, const float* zy, const uint32_t* xt,
-                           const uint32_t* hm0, const uint32_t* hm1, const fv_modeset::Tables* tab);
+int t1_xdirect_pass1_entry(fv_plan* P, const void* bx, const void* by, const int32_t* n_dev, int64_t n_cap, int nb, int ntr,
+                           const void* W, int64_t nf, int w, double beta, const fv_modeset::Tables* tab);
 
 // small-grid type-1 path (type1_small.cu)
 bool t1s_width_built(int w);

@@ -139,7 +139,7 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   const size_t per = (size_t)nb * n_cap;
   const int nstrips = ceil_div(nf, R);
   const bool masks = nstrips > 1 && nstrips <= 64;           // strip membership of every source as two 32-bit masks
-  rc = ensure(&P->prep, &P->prep_bytes, per * (5 * sizeof(int32_t) + 2 * sizeof(T)));
+  if (!use_xd) rc = ensure(&P->prep, &P->prep_bytes, per * (4 * sizeof(int32_t) + 2 * sizeof(T)));
   if (rc) return rc;
   int32_t* ix0 = (int32_t*)P->prep;
   int32_t* iy0 = ix0 + per;
@@ -147,12 +147,11 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   uint32_t* hm1 = hm0 + per;
   T* zx = (T*)(hm1 + per);
   T* zy = zx + per;
-  uint32_t* xt = (uint32_t*)(zy + per);
-  {
+  if (!use_xd) {
     StageScope ts(P, FV_STAGE_ZERO);
     dim3 grid(ceil_div(n_cap, 256), nb);
     t1_prep_kernel<T><<<grid, 256, 0, P->stream>>>((const T*)bx, (const T*)by, n_dev, n_cap, P->bp_dev, (int)nf, w, ix0, iy0, zx, zy,
-                                                   R, nstrips, masks ? hm0 : nullptr, masks ? hm1 : nullptr, use_xd ? xt : nullptr);
+                                                   R, nstrips, masks ? hm0 : nullptr, masks ? hm1 : nullptr);
     FV_LAUNCH_CHECK();
   }
   // small grid held whole in one CTA and many sources: bins of sources + register windows (type1_small.cuh)
@@ -169,9 +168,7 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
     // the strip kernel takes any transform count as well; nothing to do
   }
   if (use_xd) {
-    StageScope ts(P, FV_STAGE_SPREAD);
-    rc = t1_xdirect_pass1_entry(P, n_dev, n_cap, nb, ntr, W, nf, w, beta, iy0, (const float*)zy, xt,
-                                masks ? hm0 : nullptr, masks ? hm1 : nullptr, tab);
+    rc = t1_xdirect_pass1_entry(P, bx, by, n_dev, n_cap, nb, ntr, W, nf, w, beta, tab);
     if (rc) return rc;
   }
   if (use_small) {
@@ -223,6 +220,7 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   g.Tbuf = (const C*)P->tbuf; g.nf = (int)nf; g.pitch = pitch; g.ncols = ncols; g.cols_per_cta = cpc; g.ntr = ntr;
   g.tw = (const C*)F->tw; g.st = F->st; g.col_off = tab->col_off; g.s_k = tab->s_k; g.s_pos = tab->s_pos;
   g.s_scale = (const T*)(use_xd ? tab->s_scale_y : tab->s_scale); g.epi = make_epi(epi);
+  g.t_rowmajor = use_xd ? 1 : 0;
   {
     StageScope ts(P, FV_STAGE_GATHER);
     auto kern = t1_ffty_gather_kernel<T>;

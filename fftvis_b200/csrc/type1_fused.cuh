@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256)
 t1_prep_kernel(const T* __restrict__ bx, const T* __restrict__ by, const int32_t* __restrict__ n_dev,
                int64_t n_cap, const BatchParams* __restrict__ bp, int nf, int w, int32_t* __restrict__ ix0,
                int32_t* __restrict__ iy0, T* __restrict__ zx, T* __restrict__ zy, int R, int nstrips,
-               uint32_t* __restrict__ hm0, uint32_t* __restrict__ hm1, uint32_t* __restrict__ xt) {
+               uint32_t* __restrict__ hm0, uint32_t* __restrict__ hm1) {
   const int n = *n_dev;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
@@ -282,12 +282,6 @@ t1_prep_kernel(const T* __restrict__ bx, const T* __restrict__ by, const int32_t
   const double gy = fold_grid((double)(by[s] * smul), nf), giy = ceil(gy - hw);
   ix0[o] = (int)gix; zx[o] = (T)(gix - gx);
   iy0[o] = (int)giy; zy[o] = (T)(giy - gy);
-  if (xt) {
-    // x itself as a fraction of a turn in 32-bit fixed point (x = 0 -> 0): k * xt wraps mod one turn exactly
-    double r = (double)(bx[s] * smul) * 0.15915494309189533577;
-    r -= floor(r);
-    xt[o] = (uint32_t)(unsigned long long)(r * 4294967296.0 + 0.5);
-  }
   if (hm0) {
     // which strips (of R rows; at most 64) the w footprint rows touch, as two 32-bit masks: the strip
     // CTAs of pass 1 then test one bit per source instead of redoing the row arithmetic
@@ -708,8 +702,8 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
 
 template <typename T>
 struct T1GatherArgs {
-  const cplx_t<T>* Tbuf;         // (nb, ntr, ncols, nf)
-  int nf, pitch, ncols, cols_per_cta, ntr;
+  const cplx_t<T>* Tbuf;         // (nb, ntr, ncols, nf); (nb, ntr, nf, ncols) when t_rowmajor (x-direct pass 1)
+  int nf, pitch, ncols, cols_per_cta, ntr, t_rowmajor;
   const cplx_t<T>* tw;
   FftStages st;
   const int32_t* col_off;        // (ncols + 1) ranges into the column-sorted baseline tables
@@ -734,10 +728,21 @@ t1_ffty_gather_kernel(T1GatherArgs<T> a) {
   const C* Tb = a.Tbuf + ((int64_t)bpi * a.ncols + c0) * nf;
   // columns -> shared memory with asynchronous copies (LDGSTS): every element's load is in flight
   // at once instead of a register round trip per element
-  for (int ci = tid >> 5; ci < nc; ci += blockDim.x >> 5) {
-    const C* src = Tb + (int64_t)ci * nf;
-    C* dst = cols + ci * pitch;
-    for (int rr = tid & 31; rr < nf; rr += 32) __pipeline_memcpy_async(dst + rr, src + rr, sizeof(C));
+  if (a.t_rowmajor) {
+    // rows of nc consecutive columns: element i -> (row i / nc, column i % nc)
+    const C* Tr = a.Tbuf + (int64_t)bpi * a.ncols * nf + c0;
+    const unsigned inv_nc = nc > 1 ? 0xFFFFFFFFu / (unsigned)nc + 1u : 0u;
+    for (int i = tid; i < nc * nf; i += blockDim.x) {
+      const int rr = inv_nc ? (int)__umulhi((unsigned)i, inv_nc) : i;
+      const int ci = i - rr * nc;
+      __pipeline_memcpy_async(cols + ci * pitch + rr, Tr + (int64_t)rr * a.ncols + ci, sizeof(C));
+    }
+  } else {
+    for (int ci = tid >> 5; ci < nc; ci += blockDim.x >> 5) {
+      const C* src = Tb + (int64_t)ci * nf;
+      C* dst = cols + ci * pitch;
+      for (int rr = tid & 31; rr < nf; rr += 32) __pipeline_memcpy_async(dst + rr, src + rr, sizeof(C));
+    }
   }
   __pipeline_commit();
   for (int i = tid; i < a.st.tw_len; i += blockDim.x) tw[i] = a.tw[i];

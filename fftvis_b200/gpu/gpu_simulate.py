@@ -334,12 +334,23 @@ class GPUSimulationEngine(SimulationEngine):
             rows = max(1, min(32, (190 * 1024) // row_bytes))
             rows -= rows % 8 if rows > 8 else 0
             strips = -(-nf // rows)
-        best, best_eff = nb_max, 0.0
+        nc = ncols or n_modes
+        xdirect = precision == 1 and strips > 1 and nf >= 2 * (24 + w.value)
+        if xdirect:
+            # x-direct pass 1 (csrc/type1_xdirect.cuh): strips of 24 rows, groups of 256 columns, three CTAs per SM
+            strips, slots = -(-nf // 24) * -(-nc // 256), 3 * 148
+        else:
+            slots = 148
+        # pass 2: groups of <= 8 / 16 columns, three (single) / one (double precision) CTAs per SM
+        cpc = max(1, min(16, ((74 if precision == 1 else 100) * 1024 - nf * csize) // row_bytes))
+        cpc -= cpc % 8 if cpc >= 8 else 0
+        groups, slots2 = -(-nc // cpc), (3 if precision == 1 else 1) * 148
+        best, best_cost = nb_max, float("inf")
         for nb in range(max(1, nb_max // 2), nb_max + 1):
-            ctas = strips * nb * P
-            eff = ctas / (-(-ctas // 148) * 148)
-            if eff >= best_eff - 1e-9:
-                best, best_eff = nb, eff
+            # whole waves of both passes per frequency; a pass-1 wave weighs ~1.5 pass-2 waves (measured on cfg2)
+            cost = (1.5 * -(-strips * nb * P // slots) + (-(-groups * nb * P // slots2) if xdirect else 0)) / nb
+            if cost <= best_cost + 1e-12:
+                best, best_cost = nb, cost
         return int(best)
 
     # ------------------------------------------------------------------------------------------
