@@ -462,21 +462,29 @@ def build_roofline(args, eng, plan2, stages, n_live, hbm_peak, peak_src, w, nf_l
         ach = alg / (sp_ms / sp_n * 1e-3) / 1e9
         wk, nf = kernel_geometry(plan2)
         small = nf * (nf + 1) * c <= 160 * 1024
-        kname = (("t1_spread_fftx_kernel, whole grid per CTA" if small else
-                  "t1_spread_fftx_kernel (fused spread + FFT-x, strip of the grid in shared memory)")
-                 if eng.type1_method == "fused" else "spread_kernel (type 1, global grid)")
+        xdirect = eng.type1_method == "fused" and plan2.precision == 1 and not small and nf >= 2 * (24 + wk)
+        if eng.type1_method != "fused":
+            kname = "spread_kernel (type 1, global grid)"
+        elif xdirect:
+            kname = "t1_xdirect_kernel (pass 1 without an x grid: Fourier sum over the needed columns, gridded in y, accumulators in registers)"
+        elif small:
+            kname = "t1s_spread_kernel (whole grid per CTA, bin-sorted sources, register windows)"
+        else:
+            kname = "t1_spread_fftx_kernel (fused spread + FFT-x, strip of the grid in shared memory)"
+        real = ("on-chip (FP32 multiply-add issue + sin/cos unit): no fine grid exists, DRAM traffic is the write of T only, "
+                "so the HBM fraction is an algorithmic yardstick, not the limiter") if xdirect else \
+               ("on-chip (shared-memory pipe / instruction issue): the fine grid never leaves the SM, "
+                "so the HBM fraction is an algorithmic yardstick, not the limiter")
         traffic, on_chip = None, None
         tf = ROOT / "profiles" / "r02_traffic.json"
         if tf.exists() and eng.type1_method == "fused":
             prof = json.loads(tf.read_text())
-            traffic = prof.get(w["name"], {}).get("t1_spread_fftx_kernel")
+            traffic = prof.get(w["name"], {}).get("pass1")
             on_chip = prof.get(w["name"] + "_ncu")        # ncu: issue-active and shared-memory pipe utilisation
         return {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                 "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg, "avg_launch_ms": sp_ms / sp_n, "launches": sp_n,
-                "real_bound": "on-chip (shared-memory pipe / instruction issue): the fine grid never leaves the SM, "
-                              "so the HBM fraction is an algorithmic yardstick, not the limiter",
-                "on_chip_ncu": on_chip}
+                "real_bound": real, "on_chip_ncu": on_chip}
     # type 3: spreader and the pruned FFT passes; report the larger one
     sp_ms, sp_n = stages["spread"]
     ff_ms, ff_n = stages["fft"]

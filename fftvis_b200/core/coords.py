@@ -152,3 +152,56 @@ def enu_to_az_za(enu_e, enu_n, orientation: str = "uvbeam"):
         raise ValueError("orientation must be 'astropy' or 'uvbeam'")
     az = np.mod(az, TWO_PI)
     return az.astype(e.dtype, copy=False), za.astype(e.dtype, copy=False)
+
+
+class CoordinateRotation:
+    """The argument the reference's chunk evaluator calls ``coord_mgr`` (matvis ``CoordinateRotation``,
+    constructed at cpu_simulate.py:693-704 and consumed at :856-940): the catalogue as coherency, the
+    observation times, the site, the source positions and the chunking.  Here it only *carries* those
+    inputs -- the rotation itself is the ``fv_rotate_cut`` kernel -- so that
+    ``GPUSimulationEngine._evaluate_vis_chunk`` can be called with the reference's own keyword set.
+    ``skycoords`` is an astropy ``SkyCoord`` (duck-typed ``.ra.rad`` / ``.dec.rad``) or an ``(ra, dec)``
+    pair in radians.  A matvis manager passed instead is read through the same attribute names."""
+
+    _methods = {name: name for name in astrometry.COORD_METHODS}
+    method = "CoordinateRotationERFA"
+
+    def __init__(self, flux, times, telescope_loc, skycoords, chunk_size=None, source_buffer=1.0, precision=2,
+                 method=None, **coord_method_params):
+        self.flux = np.asarray(flux)
+        self.times = times
+        self.telescope_loc = telescope_loc
+        self.skycoords = skycoords
+        self.nsrc = int(np.shape(self.flux)[0])
+        self.chunk_size = int(chunk_size) if chunk_size else self.nsrc
+        self.source_buffer = float(source_buffer)
+        self.precision = int(precision)
+        if method is not None:
+            if method not in astrometry.COORD_METHODS:
+                raise KeyError(method)
+            self.method = method
+        self.coord_method_params = dict(coord_method_params)
+
+    def setup(self):          # matvis allocates its device/host buffers here; nothing to do
+        return None
+
+
+def manager_inputs(coord_mgr) -> dict:
+    """What ``_evaluate_vis_chunk`` needs from a ``coord_mgr`` (this module's ``CoordinateRotation`` or a
+    matvis one, duck-typed): ra/dec in radians, flux, times, site, chunk size, buffer, method + parameters."""
+    sky = coord_mgr.skycoords
+    if hasattr(sky, "ra") and hasattr(sky, "dec"):
+        ra = np.asarray(getattr(sky.ra, "rad", sky.ra), dtype=np.float64)
+        dec = np.asarray(getattr(sky.dec, "rad", sky.dec), dtype=np.float64)
+    else:
+        ra, dec = (np.asarray(v, dtype=np.float64) for v in sky)
+    method = getattr(coord_mgr, "method", None) or type(coord_mgr).__name__
+    if method not in astrometry.COORD_METHODS:
+        method = "CoordinateRotationERFA"
+    params = dict(getattr(coord_mgr, "coord_method_params", {}) or {})
+    if "update_bcrs_every" not in params and hasattr(coord_mgr, "update_bcrs_every"):
+        ub = coord_mgr.update_bcrs_every
+        params["update_bcrs_every"] = float(ub.to_value("s")) if hasattr(ub, "to_value") else float(ub)
+    return dict(ra=ra, dec=dec, flux=np.asarray(coord_mgr.flux), times=coord_mgr.times,
+                telescope_loc=coord_mgr.telescope_loc, chunk_size=int(coord_mgr.chunk_size),
+                source_buffer=float(getattr(coord_mgr, "source_buffer", 1.0)), method=method, params=params)

@@ -129,7 +129,8 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
     geo.ntx = ceil_div(nf[0], T3_TILE); geo.nty = ceil_div(nf[1], T3_TILE);
     ntiles = geo.ntx * geo.nty;
     const size_t nt1 = (size_t)ntiles + 1;
-    const size_t need = sizeof(int32_t) * (3 * nt1 + 16 * (size_t)n_cap);
+    const size_t lcap = 16 * (size_t)n_cap;                     // <= 4 x 4 tiles per source
+    const size_t need = sizeof(int32_t) * (3 * nt1 + 2 * lcap);
     rc = ensure(&P->bins, &P->bins_bytes, need); if (rc) return rc;
     bin_counts = (int32_t*)P->bins; bin_offsets = bin_counts + nt1; bin_cursor = bin_offsets + nt1; bin_list = bin_cursor + nt1;
     StageScope ts(P, FV_STAGE_ZERO);
@@ -144,6 +145,16 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
     ++fv::g_launches;
     t3_bin_kernel<T, 1><<<blocks, 256, 0, P->stream>>>(geo, nullptr, bin_offsets, bin_cursor, bin_list);
     FV_LAUNCH_CHECK();
+    // ascending source index inside every tile: a fixed summation order (the atomic cursors above are served
+    // in any order)
+    int32_t* sorted = bin_list + lcap;
+    const int nitems = (int)std::min<size_t>(lcap, (size_t)INT_MAX);
+    tmp = 0;
+    cub::DeviceSegmentedSort::SortKeys(nullptr, tmp, bin_list, sorted, nitems, ntiles, bin_offsets, bin_offsets + 1, P->stream);
+    rc = ensure(&P->scan_tmp, &P->scan_tmp_bytes, std::max<size_t>(tmp, 16)); if (rc) return rc;
+    FV_CUDA(cub::DeviceSegmentedSort::SortKeys(P->scan_tmp, tmp, bin_list, sorted, nitems, ntiles, bin_offsets, bin_offsets + 1, P->stream));
+    ++fv::g_launches;
+    bin_list = sorted;
   }
 
   // own pruned FFT passes when every padded dimension's vectors fit shared memory

@@ -6,14 +6,18 @@
 // flat, so the z extent of the grid is the minimum 2w..32 cells: here a thread OWNS one (x, y) column
 // of the grid and keeps all of its z cells in registers.
 //
-//   t3_bin_count / t3_bin_fill   counting sort of the sources into the 16 x 16-column tiles their
-//                                footprint touches (a source lands in up to 4 lists)
+//   t3_bin_kernel (count / fill) counting sort of the sources into the 16 x 16-column tiles their
+//                                footprint touches (a source lands in up to 4 lists, 9 on a grid it wraps around);
+//                                every tile's list is then sorted by source index (cub segmented sort), so the
+//                                summation order -- and the result, bit for bit -- does not depend on the order in
+//                                which the fill pass's atomic cursors were served
 //   t3_col_spread_kernel         one CTA per (tile, frequency, product), one thread per column:
 //                                walk the tile's list; a thread whose column is inside the source's
 //                                (x, y) footprint adds W k_x k_y k_z[.] to its register column; at the
 //                                end every column is stored once (plain stores: no memset, no atomics)
 #pragma once
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 #include <type_traits>
 
 namespace fv {
@@ -45,12 +49,16 @@ __device__ __forceinline__ void t3_fold(const T3Geom<T>& g, int d, T v, int* i0w
 
 // distinct tiles a w-cell footprint starting at i0w (wrapped) touches along one dimension
 __device__ __forceinline__ int t3_tiles_1d(int i0w, int w, int nf, int* out) {
-  int cnt = 0, last = -1;
+  int cnt = 0;
   for (int j = 0; j < w; ++j) {
     int c = i0w + j;
     if (c >= nf) c -= nf;
     const int t = c / T3_TILE;
-    if (t != last) { out[cnt++] = t; last = t; }
+    // a footprint that wraps around a grid of fewer than two tiles re-enters its first tile: compare with
+    // every tile emitted so far, not only the last one
+    bool seen = false;
+    for (int q = 0; q < cnt; ++q) seen |= out[q] == t;
+    if (!seen) out[cnt++] = t;
   }
   return cnt;
 }

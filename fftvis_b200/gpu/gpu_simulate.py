@@ -198,6 +198,7 @@ class GPUSimulationEngine(SimulationEngine):
         i0 = np.array([a_index[b[0]] for b in baselines], dtype=np.int64)
         i1 = np.array([a_index[b[1]] for b in baselines], dtype=np.int64)
         if not is_gridded:
+            n_modes = None
             rot = np.ascontiguousarray(core_utils.get_plane_to_xy_rotation_matrix(antvecs).T)
             rants = np.dot(rot, antvecs.T)
             bls = (rants[:, i1] - rants[:, i0]) if nbls else np.zeros((3, 0))
@@ -218,22 +219,47 @@ class GPUSimulationEngine(SimulationEngine):
         eq = params.get("eq_xyz")
         if eq is None:
             eq = coords.equatorial_unit_vectors(ra, dec)
-        eq = np.ascontiguousarray(eq, dtype=np.float64)
-
-        f_lo, f_hi = (0, nfreqs) if freq_range is None else (int(freq_range[0]), int(freq_range[1]))
         nchunks = max(1, min(int(nchunks), max(nsrc, 1)))
         chunk_size = int(math.ceil(nsrc / nchunks)) if nsrc else 0
-        n_cap = max(1, int(chunk_size * source_buffer))
+        return self._plan_from_parts(
+            dev, precision=precision, polarized=polarized, eps=eps, upsample_factor=upsample_factor,
+            beam_spline_opts=beam_spline_opts, interpolation_function=interpolation_function, freqs=freqs,
+            fluxes=fluxes if coherency is None else coherency, flux_is_coherency=coherency is not None,
+            pol_sky=pol_sky, eq=eq, enu_mats=enu_mats, astrom=astrom, bls=bls, plane=plane,
+            is_gridded=is_gridded, is_coplanar=is_coplanar, n_modes=n_modes, antnums=antnums,
+            baselines=baselines, beam_list=beam_list, beam_idx=beam_idx, beam_coefs=beam_coefs,
+            nchunks=nchunks, n_cap=max(1, int(chunk_size * source_buffer)), freq_range=freq_range)
 
+    def _plan_from_parts(self, dev, *, precision, polarized, eps, upsample_factor, beam_spline_opts,
+                         interpolation_function, freqs, fluxes, flux_is_coherency, pol_sky, eq, enu_mats, astrom,
+                         bls, plane, is_gridded, is_coplanar, n_modes, antnums, baselines, beam_list, beam_idx,
+                         beam_coefs, nchunks, n_cap, freq_range=None) -> SimulationPlan:
+        """Uploads and device tables of a plan whose host geometry is already known: the baselines ``bls``
+        (integer grid offsets of a gridded array, else seconds in the array plane), the matrix ``plane``
+        that takes ENU unit vectors to those axes, per-time ENU matrices and the catalogue.  ``prepare``
+        derives them from antenna positions (cpu_simulate.py:583-709); ``_evaluate_vis_chunk`` receives them
+        in the reference's own argument form (cpu_simulate.py:856-884).  ``flux_is_coherency``: ``fluxes`` is
+        already the coherency the reference's coordinate manager holds (0.5 I applied, cpu/utils.py:52-53)."""
+        rd, cd = _NP_R[precision], _NP_C[precision]
+        nfreqs, nbls, nsrc = int(freqs.size), len(baselines), int(np.shape(eq)[1])
+        nbeam, nant = len(beam_list), len(antnums)
+        a_index = {a: i for i, a in enumerate(antnums)}
+        i0 = np.array([a_index[b[0]] for b in baselines], dtype=np.int64)
+        i1 = np.array([a_index[b[1]] for b in baselines], dtype=np.int64)
+        eq = np.ascontiguousarray(eq, dtype=np.float64)
+        f_lo, f_hi = (0, nfreqs) if freq_range is None else (int(freq_range[0]), int(freq_range[1]))
         with torch.cuda.device(dev):
             rdt, cdt = _RDT[precision], _CDT[precision]
             eq_d = torch.as_tensor(eq).to(dev)
             # catalogue, frequency-major so that the gather through ascending src_idx coalesces
             # catalogue: uploaded as given, cast and transposed to frequency-major ON the device
             if pol_sky:
-                coh_d = torch.as_tensor(np.ascontiguousarray(coherency)).to(dev).to(cdt)
+                coh_d = torch.as_tensor(np.ascontiguousarray(fluxes)).to(dev).to(cdt)
                 flux_d = coh_d.permute(1, 2, 3, 0).reshape(nfreqs, 4, nsrc).contiguous()
+            elif flux_is_coherency:
+                flux_d = torch.as_tensor(np.ascontiguousarray(fluxes)).to(dev).to(cdt).t().contiguous()
             else:
+                # Stokes I: the 0.5 I scaling and the cast (cpu/utils.py:52-53, cpu_simulate.py:622-626)
                 raw = torch.as_tensor(np.ascontiguousarray(fluxes)).to(dev)
                 half = raw * 0.5 if raw.is_complex() else raw.to(torch.float64) * 0.5
                 del raw
@@ -643,13 +669,80 @@ class GPUSimulationEngine(SimulationEngine):
         return res.reshape(nf, nt, plan.nbls)
 
     # ------------------------------------------------------------------------------------------
-    def _evaluate_vis_chunk(self, time_idx, freq_idx, plan: SimulationPlan = None, **kwargs):
-        """One (time-slice, frequency-slice) block as ``(nt_here, nbls, nfeed, nfeed, nf_here)``
-        (cpu_simulate.py:856-1071).  The GPU engine's unit of state is the device-resident
-        ``SimulationPlan`` (from ``prepare``) instead of the CPU engine's coord_mgr / bls / beam
-        arguments."""
+    def _plan_from_chunk_args(self, beam_list, coord_mgr, rotation_matrix, antnums, baselines, bls, freqs,
+                              complex_dtype, nfeeds, beam_idx, polarized, polarized_sky_model, eps, upsample_factor,
+                              beam_spline_opts, interpolation_function, is_coplanar, use_type1, basis_matrix,
+                              type1_n_modes, nchunks, beam_coefs) -> SimulationPlan:
+        """Device plan from the reference's chunk-evaluator arguments (cpu_simulate.py:856-884)."""
+        dev = self._device()
+        m = coords.manager_inputs(coord_mgr)
+        precision = 1 if (complex_dtype is not None and np.dtype(complex_dtype) == np.complex64) else \
+            (2 if complex_dtype is not None else int(getattr(coord_mgr, "precision", 2)))
+        rd = _NP_R[precision]
+        if nfeeds is not None and int(nfeeds) != (2 if polarized else 1):
+            raise ValueError("nfeeds must be 2 for polarized and 1 for unpolarized simulations")
+        if eps is None:
+            eps = default_accuracy_dict[precision]
+        freqs = np.atleast_1d(np.asarray(freqs)).astype(rd, copy=False)
+        baselines = [tuple(b) for b in baselines]
+        if antnums is None:
+            antnums = sorted({a for b in baselines for a in b})
+        antnums = list(antnums)
+        beam_idx = core_utils.validate_beam_idx(beam_idx, beam_coefs, len(beam_list), len(antnums))
+        bls = np.asarray(bls)
+        # ENU -> the axes the baselines are expressed in (cpu_simulate.py:961-965): array-plane rotation,
+        # then the lattice basis of a gridded array (already divided by c by the caller, :676-677)
+        plane = np.eye(3) if rotation_matrix is None else np.asarray(rotation_matrix, dtype=np.float64)
+        if basis_matrix is not None:
+            plane = np.asarray(basis_matrix, dtype=np.float64).T @ plane
+        if use_type1:
+            bls = np.round(bls).astype(int)
+            n_modes = int(type1_n_modes) if type1_n_modes is not None else 2 * int(np.abs(bls).max()) + 1
+        else:
+            bls, n_modes = bls.astype(rd), None
+        flux = m["flux"]
+        pol_sky = bool(polarized_sky_model) or flux.ndim == 4
+        enu_mats, astrom = coords.coordinate_blocks(m["times"], m["telescope_loc"], m["method"], m["params"])
+        eq = m["params"].get("eq_xyz")
+        if eq is None:
+            eq = coords.equatorial_unit_vectors(m["ra"].astype(rd), m["dec"].astype(rd))
+        nsrc = int(m["ra"].size)
+        # the manager's chunk size and nchunks describe the same split (cpu_simulate.py:691, :939)
+        nchunks = max(int(nchunks), -(-nsrc // max(m["chunk_size"], 1))) if nsrc else 1
+        nchunks = max(1, min(nchunks, max(nsrc, 1)))
+        chunk_size = int(math.ceil(nsrc / nchunks)) if nsrc else 0
+        return self._plan_from_parts(
+            dev, precision=precision, polarized=polarized, eps=eps, upsample_factor=upsample_factor,
+            beam_spline_opts=beam_spline_opts, interpolation_function=interpolation_function, freqs=freqs,
+            fluxes=flux, flux_is_coherency=True, pol_sky=pol_sky, eq=eq, enu_mats=enu_mats, astrom=astrom,
+            bls=bls, plane=plane, is_gridded=bool(use_type1), is_coplanar=bool(is_coplanar) or bool(use_type1),
+            n_modes=n_modes, antnums=antnums, baselines=baselines, beam_list=beam_list, beam_idx=beam_idx,
+            beam_coefs=beam_coefs, nchunks=nchunks, n_cap=max(1, int(chunk_size * m["source_buffer"])))
+
+    def _evaluate_vis_chunk(self, time_idx, freq_idx, beam_list=None, coord_mgr=None, rotation_matrix=None,
+                            antnums=None, baselines=None, bls=None, freqs=None, complex_dtype=None, nfeeds=None,
+                            beam_idx=None, polarized=False, polarized_sky_model=False, eps=None,
+                            upsample_factor=2, beam_spline_opts=None,
+                            interpolation_function="az_za_map_coordinates", n_threads=1, is_coplanar=False,
+                            use_type1=False, basis_matrix=None, type1_n_modes=None, trace_mem=False, nchunks=1,
+                            beam_coefs=None, plan: SimulationPlan = None):
+        """One (time-slice, frequency-slice) block as ``(nt_here, nbls, nfeed, nfeed, nf_here)``; the CPU
+        engine's signature (cpu_simulate.py:856-884, called directly by tests/test_cpu_simulate.py:1068-1087).
+
+        Two call forms.  The reference's: ``coord_mgr`` (``core.coords.CoordinateRotation`` or a matvis
+        manager: catalogue, times, site, source positions, chunking), the baselines ``bls`` in the array
+        plane with ``rotation_matrix`` (type 3) or as integer grid offsets with ``basis_matrix`` /
+        ``type1_n_modes`` (type 1), exactly as ``simulate`` hands them to its workers; a device plan is
+        built from them.  Or ``plan=<SimulationPlan from prepare()>``: the GPU engine's own unit of state,
+        which skips the uploads.  ``n_threads`` and ``trace_mem`` are CPU knobs and are ignored."""
         if plan is None:
-            raise TypeError("GPUSimulationEngine._evaluate_vis_chunk needs plan=<SimulationPlan from prepare()>")
+            if coord_mgr is None or beam_list is None or bls is None or freqs is None or baselines is None:
+                raise TypeError("_evaluate_vis_chunk needs either plan=<SimulationPlan> or the reference's "
+                                "arguments (beam_list, coord_mgr, rotation_matrix, antnums, baselines, bls, freqs, ...)")
+            plan = self._plan_from_chunk_args(
+                beam_list, coord_mgr, rotation_matrix, antnums, baselines, bls, freqs, complex_dtype, nfeeds,
+                beam_idx, polarized, polarized_sky_model, eps, upsample_factor, beam_spline_opts,
+                interpolation_function, is_coplanar, use_type1, basis_matrix, type1_n_modes, nchunks, beam_coefs)
         nt_all, nf_all = plan.ntimes, plan.freqs_host.size
         ts = range(nt_all)[time_idx]
         fs = range(nf_all)[freq_idx]

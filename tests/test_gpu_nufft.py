@@ -221,13 +221,15 @@ def test_type3_3d_tiled_spreader_matches_atomic_spreader_and_direct_sum(prec, ep
     n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
     plan = default_plan()
     outs = []
-    for tiles in (1, 0):
+    for tiles in (1, 0, 1, 1):
         plan.set_option("t3_tiles", tiles)
         out = torch.zeros((nb, ntr, nk), dtype=cdt, device="cuda")
         epi = _lib.make_epilogue(out.data_ptr(), out.stride(0), out.stride(1))
         plan.type3(prec, 3, xs, n_dev, None, us, None, scale, Wd, eps, 2.0, epi)
         outs.append(out.cpu().numpy())
     plan.set_option("t3_tiles", 1)
+    # tile lists are sorted by source index: the tiled spreader's sums are bitwise reproducible
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[0], outs[3])
     for b in range(nb):
         uu = [(a * rd(scale[b])).astype(rd) for a in u]
         want = nc.direct_sum(x[0], x[1], x[2], W[b], uu[0], uu[1], uu[2])
@@ -411,3 +413,20 @@ def test_type1_xdirect_pass1(eps, n_modes, ntr, nk):
     assert not np.array_equal(got, old)          # the two pass-1 kernels really are different code paths
     again = gpu_nufft2d_type1(x, y, c, n_modes, idx, eps, method="fused")
     assert np.array_equal(got, again)            # fixed summation order: bitwise reproducible
+
+
+@pytest.mark.parametrize("extent", [0.4, 1.2, 3.0])
+def test_type3_3d_tiny_grids_wrapping_footprints(extent):
+    """Very short baselines give 3-D type-3 grids of 16..32 cells per side, where a kernel footprint wraps
+    around the grid and re-enters its first tile: every source must still be spread exactly once."""
+    from fftvis_b200.gpu import gpu_nufft3d
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(int(extent * 10))
+    n, nk, eps = 3000, 40, 1e-9
+    lm = rng.uniform(-0.7, 0.7, (2, n))
+    x = [2 * np.pi * lm[0], 2 * np.pi * lm[1], 2 * np.pi * np.sqrt(1 - (lm**2).sum(0))]
+    u = [rng.uniform(-extent, extent, nk), rng.uniform(-extent, extent, nk), rng.uniform(-0.05, 0.05, nk)]
+    c = rng.normal(size=(1, n)) + 1j * rng.normal(size=(1, n))
+    got = gpu_nufft3d(x[0], x[1], x[2], c, u[0], u[1], u[2], eps)
+    want = nc.direct_sum(x[0], x[1], x[2], c, u[0], u[1], u[2])
+    assert relerr(got, want) < 10 * eps

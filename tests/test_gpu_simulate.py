@@ -159,6 +159,58 @@ def test_evaluate_vis_chunk_slices_match_simulate():
     np.testing.assert_allclose(blk[0, :, 0, 0, :].T, full[2:5, 1], rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("gridded", [False, True])
+@pytest.mark.parametrize("polarized", [False, True])
+def test_evaluate_vis_chunk_reference_call_form(gridded, polarized):
+    """The chunk evaluator called the way the reference's own test calls the CPU engine
+    (/root/reference/tests/test_cpu_simulate.py:1036-1087): coordinate manager + plane-rotated baselines in
+    seconds (type 3) or integer lattice offsets with the basis matrix (type 1), against ``simulate``."""
+    from fftvis_b200 import GaussianBeam, HERA_LOCATION
+    from fftvis_b200.core import antenna_gridding, utils
+    from fftvis_b200.core.coords import CoordinateRotation
+    from fftvis_b200.gpu import GPUSimulationEngine
+    ants = hex_ants(2)
+    if not gridded:                       # a perturbed hex is not a lattice: type 3
+        rng = np.random.default_rng(5)
+        ants = {k: v + np.r_[rng.uniform(-0.4, 0.4, 2), 0.0] for k, v in ants.items()}
+    freqs = np.linspace(100e6, 120e6, 4)
+    ra, dec, flux = small_sky(150, freqs)
+    beam = GaussianBeam(diameter=14.0)
+    beam = beam if polarized else beam.to_power()
+    eng = GPUSimulationEngine()
+    full = eng.simulate(ants, freqs, flux, [beam], ra, dec, TIMES, HERA_LOCATION, precision=2, eps=1e-12,
+                        polarized=polarized)
+    # ---- the front half of simulate, restated as the reference's test does
+    baselines = [r[0] for r in utils.get_pos_reds(ants, include_autos=True)]
+    antnums = list(ants.keys())
+    antvecs = np.array([ants[a] for a in antnums], dtype=np.float64)
+    coord_mgr = CoordinateRotation._methods["CoordinateRotationERFA"]
+    coord_mgr = CoordinateRotation(flux=0.5 * flux, times=TIMES, telescope_loc=HERA_LOCATION, skycoords=(ra, dec),
+                                   precision=2, source_buffer=1.0, chunk_size=ra.size, method=coord_mgr)
+    if gridded:
+        ok, gpos, basis = antenna_gridding.check_antpos_griddability(ants)
+        assert ok
+        bls = np.round(np.array([gpos[b[1]] - gpos[b[0]] for b in baselines]).T).astype(int)
+        kw = dict(rotation_matrix=np.eye(3), bls=bls, use_type1=True, basis_matrix=basis / utils.speed_of_light,
+                  type1_n_modes=2 * int(np.abs(bls).max()) + 1, is_coplanar=True)
+    else:
+        rot = np.ascontiguousarray(utils.get_plane_to_xy_rotation_matrix(antvecs).T)
+        rants = rot @ antvecs.T
+        idx = {a: i for i, a in enumerate(antnums)}
+        bls = np.array([rants[:, idx[b[1]]] - rants[:, idx[b[0]]] for b in baselines]).T / utils.speed_of_light
+        kw = dict(rotation_matrix=rot, bls=bls, is_coplanar=True)
+    nf = 2 if polarized else 1
+    blk = eng._evaluate_vis_chunk(
+        time_idx=slice(None), freq_idx=slice(1, 4), beam_list=[beam], coord_mgr=coord_mgr, antnums=antnums,
+        baselines=baselines, freqs=freqs, complex_dtype=np.complex128, nfeeds=nf, polarized=polarized, eps=1e-12,
+        beam_spline_opts=None, interpolation_function="az_za_map_coordinates", n_threads=1, trace_mem=False, **kw)
+    assert blk.shape == (len(TIMES), len(baselines), nf, nf, 3)
+    want = full[1:4].reshape(3, len(TIMES), nf, nf, len(baselines))
+    np.testing.assert_allclose(np.transpose(blk, (4, 0, 2, 3, 1)), want, rtol=1e-10, atol=1e-10 * np.abs(want).max())
+    with pytest.raises(TypeError, match="plan="):
+        eng._evaluate_vis_chunk(slice(None), slice(None))
+
+
 def test_cubic_spline_beam_matches_cpu_pipeline():
     """beam_spline_opts={"order": 3}: cubic B-spline interpolation of the UVBeam table (host prefilter,
     device 4 x 4 taps) against scipy's map_coordinates inside the CPU pipeline."""
