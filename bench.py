@@ -207,7 +207,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = make_workload(args.workload, args.nfreq, args.ntimes, args.nsrc)
+    w = apply_overrides(make_workload(args.workload, args.nfreq, args.ntimes, args.nsrc), args)
     nbls = n_baselines(w)
     vals, secs, sample, cores = [], [], "", 1
     for i in range(args.warmup + args.steps):
@@ -283,10 +283,15 @@ def run_gpu(args):
         w = make_workload(args.workload, args.nfreq, args.ntimes, args.nsrc, freq_range=shards[rank])
     else:
         w = make_workload(args.workload, args.nfreq, args.ntimes, args.nsrc, time_block=rank)
+    w = apply_overrides(w, args)
     nbls = n_baselines(w)
     beam = w["beam"] if w["polarized"] else w["beam"].to_power()
     beam_list = beam if isinstance(beam, list) else [beam]
     eng = GPUSimulationEngine(freq_batch=args.freq_batch, type1_method=args.type1_method)
+    if args.no_beam_tiles:
+        eng.beam_tiles = False
+    elif os.environ.get("FV_BEAM_TILES"):                    # "sort" (default) or "smem"
+        eng.beam_tiles = True if os.environ["FV_BEAM_TILES"] == "smem" else os.environ["FV_BEAM_TILES"]
     plan = eng.prepare(w["ants"], w["freqs"], w["fluxes"], beam_list, w["ra"], w["dec"], w["times"],
                        w["telescope_loc"], precision=w["precision"], polarized=w["polarized"], **w["kwargs"])
     P = 4 if plan.polarized else 1
@@ -316,6 +321,8 @@ def run_gpu(args):
     barrier()
     nufft.set_timing(True)
     nufft.reset_timing()
+    eng.time_stages = True
+    eng.stage_times()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -332,6 +339,8 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     stages = nufft.stage_times()
     nufft.set_timing(False)
+    stages.update(eng.stage_times())                     # rotate + cut, beam-tile sort, weights
+    eng.time_stages = False
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -439,6 +448,14 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def apply_overrides(w, args):
+    """Command-line overrides of a workload's simulate() keywords."""
+    if getattr(args, "force_type3", False):
+        w["kwargs"] = dict(w["kwargs"], force_use_type3=True)
+        w["desc"] += " [force_use_type3]"
+    return w
+
+
 def make_workload_nfreq(args) -> int:
     return int(args.nfreq or {"cfg1": 2, "cfg2": 1024, "cfg3": 1024, "cfg4": 512, "cfg5": 1024}[args.workload])
 
@@ -530,6 +547,10 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = one workload frequency-sharded with the NCCL gather (default); "
                          "weak = every rank the whole workload on its own block of times")
+    ap.add_argument("--force-type3", action="store_true",
+                    help="type-3 transforms even for a gridded array (the reference's force_use_type3)")
+    ap.add_argument("--no-beam-tiles", action="store_true",
+                    help="table beams gathered from global memory instead of staged in shared memory")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffers) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

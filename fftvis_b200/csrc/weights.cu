@@ -8,6 +8,8 @@
 // stored frequency-major so that the gather through src_idx (ascending) is coalesced.
 #include "common.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 namespace fv {
 
 constexpr double kC = 299792458.0;
@@ -17,6 +19,33 @@ struct BeamVal { double re[4], im[4]; };   // efield: [vec*2+feed]; power: re[0]
 template <typename T> struct tab_elem;      // how table entries are stored
 template <> struct tab_elem<float> { using real = float; using cplx = float2; };
 template <> struct tab_elem<double> { using real = double; using cplx = double2; };
+
+// grid index of a direction on an az/za table (fractional; azimuth wrapped and shifted into the host's
+// wrap-extended axis)
+__device__ __forceinline__ void table_index(const fv_beam& b, double az, double za, double& zi, double& ai) {
+  zi = (za - b.za0) / b.dza;
+  ai = (az - b.az0) / b.daz;
+  if (b.az_wrap_period > 0) {
+    ai = fmod(ai, (double)b.az_wrap_period);
+    if (ai < 0) ai += (double)b.az_wrap_period;
+    ai += (double)b.az_pad;
+  }
+}
+
+// the (up to) four taps and weights of orders 0 / 1, mode 'nearest' outside the grid
+__device__ __forceinline__ void table_taps(const fv_beam& b, double zi, double ai, int& z0, int& z1, int& a0, int& a1,
+                                           double& wz, double& wa) {
+  if (b.order == 0) {
+    z0 = z1 = min(max((int)floor(zi + 0.5), 0), b.nza - 1);
+    a0 = a1 = min(max((int)floor(ai + 0.5), 0), b.naz - 1);
+    wz = wa = 0.0;
+  } else {
+    const double zf = floor(zi), af = floor(ai);
+    wz = zi - zf; wa = ai - af;
+    z0 = min(max((int)zf, 0), b.nza - 1); z1 = min(max((int)zf + 1, 0), b.nza - 1);
+    a0 = min(max((int)af, 0), b.naz - 1); a1 = min(max((int)af + 1, 0), b.naz - 1);
+  }
+}
 
 template <typename T>
 __device__ inline void eval_beam(const fv_beam& b, double az, double za, double freq, int fb,
@@ -42,13 +71,8 @@ __device__ inline void eval_beam(const fv_beam& b, double az, double za, double 
     return;
   }
   // ---- az/za table, mode 'nearest' outside the grid (scipy.ndimage.map_coordinates semantics)
-  double zi = (za - b.za0) / b.dza;
-  double ai = (az - b.az0) / b.daz;
-  if (b.az_wrap_period > 0) {
-    ai = fmod(ai, (double)b.az_wrap_period);
-    if (ai < 0) ai += (double)b.az_wrap_period;
-    ai += (double)b.az_pad;
-  }
+  double zi, ai;
+  table_index(b, az, za, zi, ai);
   const int ncomp = b.is_power ? 1 : 4;
   const int64_t plane = (int64_t)b.nza * b.naz;
   const int fi = b.freq_offset + fb;
@@ -97,16 +121,7 @@ __device__ inline void eval_beam(const fv_beam& b, double az, double za, double 
   }
   int z0, z1, a0, a1;
   double wz, wa;
-  if (b.order == 0) {
-    z0 = z1 = min(max((int)floor(zi + 0.5), 0), b.nza - 1);
-    a0 = a1 = min(max((int)floor(ai + 0.5), 0), b.naz - 1);
-    wz = wa = 0.0;
-  } else {
-    const double zf = floor(zi), af = floor(ai);
-    wz = zi - zf; wa = ai - af;
-    z0 = min(max((int)zf, 0), b.nza - 1); z1 = min(max((int)zf + 1, 0), b.nza - 1);
-    a0 = min(max((int)af, 0), b.naz - 1); a1 = min(max((int)af + 1, 0), b.naz - 1);
-  }
+  table_taps(b, zi, ai, z0, z1, a0, a1, wz, wa);
   const double w00 = (1 - wz) * (1 - wa), w01 = (1 - wz) * wa, w10 = wz * (1 - wa), w11 = wz * wa;
   // nfreq_table is implied by the caller's indexing: plane stride per (comp, freq)
   for (int c = 0; c < ncomp; ++c) {
@@ -162,7 +177,7 @@ __device__ __forceinline__ void coherency_product(int mode, const cplx_t<T>* Ai,
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 weights_kernel(int mode, fv_beam bi, fv_beam bj, int same_beam, const T* __restrict__ az,
                const T* __restrict__ za, const int32_t* __restrict__ src_idx,
                const int32_t* __restrict__ n_dev, int64_t n_cap, const double* __restrict__ freqs,
@@ -239,7 +254,7 @@ constexpr int kMaxBasis = 8;
 struct BeamSet { fv_beam b[kMaxBasis]; int K; };
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 weights_basis_kernel(int mode, BeamSet bs, const T* __restrict__ az, const T* __restrict__ za,
                      const int32_t* __restrict__ src_idx, const int32_t* __restrict__ n_dev, int64_t n_cap,
                      const double* __restrict__ freqs, int64_t f0, const cplx_t<T>* __restrict__ flux,
@@ -284,6 +299,77 @@ weights_basis_kernel(int mode, BeamSet bs, const T* __restrict__ az, const T* __
         ++q;
       }
     }
+}
+
+}  // namespace fv
+
+#include "weights_tiled.cuh"
+
+// sorted-by-tile state of one time step's live set (fv_tiles_*)
+struct fv_tiles {
+  cudaStream_t stream = nullptr;
+  void* sortbuf = nullptr; size_t sort_bytes = 0;      // keys, vals, sorted keys, sorted vals (n_cap each)
+  void* scratch = nullptr; size_t scratch_bytes = 0;   // permuted copy of the live set
+  void* cub_tmp = nullptr; size_t cub_bytes = 0;
+  int32_t* tile_off = nullptr; int off_cap = 0;
+  fv_beam geom{};                                      // grid the tiles were built for
+  int ntiles = 0; int64_t n_cap = 0; bool valid = false;
+};
+
+namespace fv {
+
+static int grow(void** p, size_t* have, size_t need) {
+  if (*have >= need) return FV_OK;
+  if (*p) FV_CUDA(cudaFree(*p));
+  *p = nullptr; *have = 0;
+  FV_CUDA(cudaMalloc(p, need));
+  *have = need;
+  return FV_OK;
+}
+
+static bool same_table_grid(const fv_beam& a, const fv_beam& b) {
+  return a.kind == 3 && b.kind == 3 && a.nza == b.nza && a.naz == b.naz && a.az_wrap_period == b.az_wrap_period &&
+         a.az_pad == b.az_pad && a.az0 == b.az0 && a.daz == b.daz && a.za0 == b.za0 && a.dza == b.dza &&
+         a.order == b.order && a.is_power == b.is_power;
+}
+
+template <typename T, typename E, int NC>
+static int launch_weights_tiled(const WtArgs<T>& a_in, int ntiles, cudaStream_t st) {
+  WtArgs<T> a = a_in;
+  const size_t per_stage = (size_t)a.K * NC * WT_PTS * WT_PTS * sizeof(E);
+  a.nstage = (int)std::max<size_t>(2, std::min<size_t>(WT_MAXSTAGE, (size_t)(100 * 1024) / per_stage));
+  const size_t smem = a.nstage * per_stage;
+  dim3 grid(ntiles, ceil_div(a.nf, a.freqs_per_cta));
+#define FV_WT_LAUNCH(KM)                                                                               \
+  {                                                                                                    \
+    auto kern = weights_tiled_kernel<T, E, NC, KM>;                                                    \
+    FV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    kern<<<grid, WT_THREADS, smem, st>>>(a);                                                           \
+  }
+  if (a.K <= 2) FV_WT_LAUNCH(2) else if (a.K <= 5) FV_WT_LAUNCH(5) else FV_WT_LAUNCH(6)
+#undef FV_WT_LAUNCH
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+template <typename T>
+static int weights_tiled_impl(fv_tiles* h, int mode, const fv_beam* beams, int K, int basis, const void* az,
+                              const void* za, const int32_t* src_idx, int64_t n_cap, const double* freqs, int nf,
+                              int64_t f0, const void* flux, int64_t nsrc_total, void* out) {
+  WtArgs<T> a{};
+  a.mode = mode; a.K = K; a.basis = basis;
+  for (int k = 0; k < 8; ++k) a.b[k] = beams[k < K ? k : 0];
+  a.tile_off = h->tile_off; a.az = (const T*)az; a.za = (const T*)za; a.src_idx = src_idx; a.n_cap = n_cap;
+  a.freqs = freqs; a.f0 = f0; a.nf = nf;
+  // enough CTAs to fill the GPU a few times over, long enough runs of frequencies to pipeline the patches
+  a.freqs_per_cta = std::max(4, (int)ceil_div((int64_t)nf * h->ntiles, 8 * kNumSMs));
+  a.flux = (const cplx_t<T>*)flux; a.nsrc_total = nsrc_total; a.out = (cplx_t<T>*)out;
+  if (beams[0].is_power) {
+    a.bulk = 0;
+    return launch_weights_tiled<T, T, 1>(a, h->ntiles, h->stream);
+  }
+  a.bulk = sizeof(cplx_t<T>) == 16 ? 1 : 0;
+  return launch_weights_tiled<T, cplx_t<T>, 4>(a, h->ntiles, h->stream);
 }
 
 static bool same_beam_desc(const fv_beam& a, const fv_beam& b) {
@@ -389,4 +475,108 @@ extern "C" int fv_coherency(int prec, int mode, const void* beam_i, const void* 
     fv::coherency_kernel<double><<<blocks, 256, 0, st>>>(mode, (const double2*)beam_i, (const double2*)beam_j, (const double2*)flux_or_coh, n, (double2*)out);
   FV_LAUNCH_CHECK();
   return FV_OK;
+}
+
+/* ---- beam tables staged in shared memory (weights_tiled.cuh) ----------------------------------- */
+extern "C" int fv_tiles_create(fv_tiles** h, void* stream) {
+  FV_REQUIRE(h, "null pointer");
+  *h = new fv_tiles();
+  (*h)->stream = (cudaStream_t)stream;
+  return FV_OK;
+}
+
+extern "C" int fv_tiles_destroy(fv_tiles* h) {
+  if (!h) return FV_OK;
+  if (h->sortbuf) cudaFree(h->sortbuf);
+  if (h->scratch) cudaFree(h->scratch);
+  if (h->cub_tmp) cudaFree(h->cub_tmp);
+  if (h->tile_off) cudaFree(h->tile_off);
+  delete h;
+  return FV_OK;
+}
+
+extern "C" int fv_tiles_supported(const fv_beam* beams_host, int K) {
+  if (!beams_host || K < 1 || K > 6) return 0;
+  for (int k = 0; k < K; ++k) {
+    const fv_beam& b = beams_host[k];
+    if (b.kind != 3 || !(b.order == 0 || b.order == 1) || !fv::same_table_grid(beams_host[0], b)) return 0;
+  }
+  return 1;
+}
+
+template <typename T>
+static int tiles_sort_impl(fv_tiles* h, const fv_beam& b, void* xyz, void* az, void* za, int32_t* src_idx,
+                           const int32_t* n_dev, int64_t n_cap) {
+  using namespace fv;
+  const TileGrid g = tile_grid(b);
+  const int ntiles = g.ntz * g.nta;
+  int rc = grow(&h->sortbuf, &h->sort_bytes, 16 * (size_t)n_cap);
+  if (rc) return rc;
+  rc = grow(&h->scratch, &h->scratch_bytes, (5 * sizeof(T) + 4) * (size_t)n_cap);
+  if (rc) return rc;
+  if (h->off_cap < ntiles + 1) {
+    if (h->tile_off) FV_CUDA(cudaFree(h->tile_off));
+    FV_CUDA(cudaMalloc((void**)&h->tile_off, sizeof(int32_t) * (ntiles + 1)));
+    h->off_cap = ntiles + 1;
+  }
+  uint32_t* keys = (uint32_t*)h->sortbuf;
+  int32_t* vals = (int32_t*)(keys + n_cap);
+  uint32_t* skeys = (uint32_t*)(vals + n_cap);
+  int32_t* svals = (int32_t*)(skeys + n_cap);
+  const int blocks = ceil_div(n_cap, 256);
+  tile_key_kernel<T><<<blocks, 256, 0, h->stream>>>(b, (const T*)az, (const T*)za, n_dev, n_cap, keys, vals);
+  FV_LAUNCH_CHECK();
+  int end_bit = 1;
+  while ((1ll << end_bit) <= ntiles) ++end_bit;
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys, skeys, vals, svals, (int)n_cap, 0, end_bit, h->stream);
+  rc = grow(&h->cub_tmp, &h->cub_bytes, std::max<size_t>(tmp, 16));
+  if (rc) return rc;
+  FV_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, keys, skeys, vals, svals, (int)n_cap, 0, end_bit, h->stream));
+  ++g_launches;
+  tile_bounds_kernel<<<ceil_div(n_cap + 1, 256), 256, 0, h->stream>>>(skeys, n_cap, (uint32_t)ntiles, h->tile_off);
+  FV_LAUNCH_CHECK();
+  T* o_xyz = (T*)h->scratch;
+  T* o_az = o_xyz + 3 * n_cap;
+  T* o_za = o_az + n_cap;
+  int32_t* o_src = (int32_t*)(o_za + n_cap);
+  tile_permute_kernel<T><<<blocks, 256, 0, h->stream>>>(svals, n_dev, n_cap, (const T*)xyz, (const T*)az, (const T*)za,
+                                                     src_idx, o_xyz, o_az, o_za, o_src);
+  FV_LAUNCH_CHECK();
+  // dead slots keep whatever they held (nothing reads them): copy back the whole arrays
+  FV_CUDA(cudaMemcpyAsync(xyz, o_xyz, sizeof(T) * 3 * n_cap, cudaMemcpyDeviceToDevice, h->stream));
+  FV_CUDA(cudaMemcpyAsync(az, o_az, sizeof(T) * n_cap, cudaMemcpyDeviceToDevice, h->stream));
+  FV_CUDA(cudaMemcpyAsync(za, o_za, sizeof(T) * n_cap, cudaMemcpyDeviceToDevice, h->stream));
+  FV_CUDA(cudaMemcpyAsync(src_idx, o_src, sizeof(int32_t) * n_cap, cudaMemcpyDeviceToDevice, h->stream));
+  h->geom = b; h->ntiles = ntiles; h->n_cap = n_cap; h->valid = true;
+  return FV_OK;
+}
+
+extern "C" int fv_tiles_sort(fv_tiles* h, int prec, const fv_beam* beam_host, void* xyz, void* az, void* za,
+                             int32_t* src_idx, const int32_t* n_dev, int64_t n_cap) {
+  FV_REQUIRE(h && beam_host && xyz && az && za && src_idx && n_dev, "null pointer");
+  FV_REQUIRE(prec == 1 || prec == 2, "prec must be 1 or 2");
+  FV_REQUIRE(fv_tiles_supported(beam_host, 1), "tiles need an az/za table beam of order 0 or 1");
+  FV_REQUIRE(n_cap > 0 && n_cap < (1ll << 31), "bad n_cap");
+  if (prec == 1) return tiles_sort_impl<float>(h, *beam_host, xyz, az, za, src_idx, n_dev, n_cap);
+  return tiles_sort_impl<double>(h, *beam_host, xyz, az, za, src_idx, n_dev, n_cap);
+}
+
+extern "C" int fv_weights_tiled(fv_tiles* h, int prec, int mode, const fv_beam* beams_host, int K, int basis,
+                                const void* az, const void* za, const int32_t* src_idx, int64_t n_cap,
+                                const double* freqs, int nf, int64_t freq_index0, const void* flux, int64_t nsrc_total,
+                                void* out) {
+  FV_REQUIRE(h && beams_host && az && za && src_idx && freqs && flux && out, "null pointer");
+  FV_REQUIRE(prec == 1 || prec == 2, "prec must be 1 or 2");
+  FV_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+  FV_REQUIRE(h->valid && h->n_cap == n_cap, "fv_tiles_sort has not been run for this live set");
+  FV_REQUIRE(fv_tiles_supported(beams_host, K) && fv::same_table_grid(h->geom, beams_host[0]),
+             "beams do not share the grid the tiles were built for");
+  FV_REQUIRE(!basis || (mode != 0 && K >= 1), "the basis form is polarised");
+  FV_REQUIRE(basis || K <= 2, "the pair form takes one or two beams");
+  FV_REQUIRE((mode == 0) == (beams_host[0].is_power != 0), "mode 0 needs power beams, modes 1/2 need E-field beams");
+  if (nf == 0) return FV_OK;
+  if (prec == 1)
+    return fv::weights_tiled_impl<float>(h, mode, beams_host, K, basis, az, za, src_idx, n_cap, freqs, nf, freq_index0, flux, nsrc_total, out);
+  return fv::weights_tiled_impl<double>(h, mode, beams_host, K, basis, az, za, src_idx, n_cap, freqs, nf, freq_index0, flux, nsrc_total, out);
 }

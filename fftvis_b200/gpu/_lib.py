@@ -53,6 +53,13 @@ _SIGNATURES = {
     "fv_weights_basis": (c_int, [c_int, c_int, POINTER(fv_beam), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "fv_coherency": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "fv_tiles_create": (c_int, [POINTER(c_void_p), c_void_p]),
+    "fv_tiles_destroy": (c_int, [c_void_p]),
+    "fv_tiles_supported": (c_int, [POINTER(fv_beam), c_int]),
+    "fv_tiles_sort": (c_int, [c_void_p, c_int, POINTER(fv_beam), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_int64]),
+    "fv_weights_tiled": (c_int, [c_void_p, c_int, c_int, POINTER(fv_beam), c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "fv_plan_create": (c_int, [POINTER(c_void_p), c_void_p]),
     "fv_plan_destroy": (c_int, [c_void_p]),
     "fv_plan_set_timing": (c_int, [c_void_p, c_int]),

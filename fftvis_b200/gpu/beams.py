@@ -135,6 +135,50 @@ def launch_weights(prec, mode, beam_i: DeviceBeam, beam_j: DeviceBeam, az, za, s
         "fv_weights")
 
 
+class BeamTiles:
+    """Sorted-by-beam-tile state of one time step's live set (``fv_tiles_*``, csrc/weights_tiled.cuh): owns the
+    sort buffers; ``sort`` re-orders the live set in place, ``weights`` evaluates table beams from shared memory."""
+
+    def __init__(self, stream=None):
+        self._h = ctypes.c_void_p()
+        st = (stream or torch.cuda.current_stream()).cuda_stream
+        _lib.check(_lib.lib().fv_tiles_create(ctypes.byref(self._h), st), "fv_tiles_create")
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().fv_tiles_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _array(beams, f0):
+        arr = (_lib.fv_beam * len(beams))()
+        for k, b in enumerate(beams):
+            d = b.descriptor(f0)
+            ctypes.memmove(ctypes.byref(arr[k]), ctypes.byref(d), ctypes.sizeof(d))
+        return arr
+
+    @classmethod
+    def supported(cls, beams) -> bool:
+        """All beams are az/za tables of order 0 / 1 on one grid (at most 6 staged together)."""
+        if not beams or any(b.table is None for b in beams):
+            return False
+        return bool(_lib.lib().fv_tiles_supported(cls._array(beams, 0), len(beams)))
+
+    def sort(self, prec, beam, xyz, az, za, src_idx, n_dev, n_cap):
+        d = beam.descriptor(0)
+        _lib.check(_lib.lib().fv_tiles_sort(self._h, prec, ctypes.byref(d), xyz.data_ptr(), az.data_ptr(),
+                                            za.data_ptr(), src_idx.data_ptr(), n_dev.data_ptr(), n_cap), "fv_tiles_sort")
+
+    def weights(self, prec, mode, beams, basis, az, za, src_idx, n_cap, freqs_dev, f0, nf, flux, nsrc_total, out):
+        _lib.check(_lib.lib().fv_weights_tiled(
+            self._h, prec, mode, self._array(beams, f0), len(beams), 1 if basis else 0, az.data_ptr(), za.data_ptr(),
+            src_idx.data_ptr(), n_cap, freqs_dev.data_ptr(), nf, f0, flux.data_ptr(), nsrc_total, out.data_ptr()),
+            "fv_weights_tiled")
+
+
 def launch_weights_basis(prec, mode, beams, az, za, src_idx, n_dev, n_cap, freqs_dev, f0, nf, flux, nsrc_total,
                          out, stream=None):
     """``fv_weights_basis``: the K basis beams evaluated once per (source, frequency), all K (K + 1) / 2

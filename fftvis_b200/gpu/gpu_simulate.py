@@ -35,7 +35,7 @@ from ..core import antenna_gridding, catalog, coords
 from ..core import utils as core_utils
 from ..core.simulate import SimulationEngine, default_accuracy_dict
 from . import _lib
-from .beams import DeviceBeam, GPUBeamEvaluator, launch_weights, launch_weights_basis, resolve_interpolation
+from .beams import BeamTiles, DeviceBeam, GPUBeamEvaluator, launch_weights, launch_weights_basis, resolve_interpolation
 from .nufft import ModeSet, NufftPlan, default_plan
 
 logger = logging.getLogger(__name__)
@@ -132,8 +132,38 @@ class GPUSimulationEngine(SimulationEngine):
         self.grid_budget_bytes = int(grid_budget_bytes)
         self.last_fft_ms = None
         self._nufft = None
+        # table beams of order 0 / 1: "sort" = sort the live set by beam-grid tile, taps gathered from global
+        # memory by neighbouring threads (measured fastest: the weights kernels are bound by their fp64
+        # arithmetic at low occupancy, not by table traffic); True = patches staged in shared memory by bulk
+        # copies (csrc/weights_tiled.cuh); False = catalogue order
+        self.beam_tiles = "sort"
+        # per-stage device time of the stages outside the NUFFT plan (rotate + cut, tile sort, weights): CUDA
+        # events around every launch while ``time_stages`` is set (bench.py); read with ``stage_times()``
+        self.time_stages = False
+        self._stage_events = []
 
     # ------------------------------------------------------------------------------------------
+    def _timed(self, name, st, fn, *a, **k):
+        if not self.time_stages:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        r = fn(*a, **k)
+        e1.record(st)
+        self._stage_events.append((name, e0, e1))
+        return r
+
+    def stage_times(self, reset=True) -> dict:
+        """``{stage: (milliseconds, launches)}`` of the engine-level stages recorded since the last reset."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self._stage_events:
+            ms, n = out.get(name, (0.0, 0))
+            out[name] = (ms + e0.elapsed_time(e1), n + 1)
+        if reset:
+            self._stage_events = []
+        return out
+
     def _device(self) -> torch.device:
         _lib.require_gpu()
         if self.device is not None:
@@ -397,6 +427,15 @@ class GPUSimulationEngine(SimulationEngine):
         sb = int(_lib.lib().fv_rotate_cut_scratch_bytes(max(plan.nsrc, 1)))
         w["scratch"] = torch.empty(sb, dtype=torch.uint8, device=dev)
         w["W"] = torch.empty((nb, P, n_cap), dtype=cdt, device=dev)
+        # beam tables staged in shared memory: every beam of the plan a table of order 0 / 1 on one grid
+        # (the basis path stages its K <= 5 beams together; more than 5 go pair by pair through fv_weights)
+        nbm = len(plan.beams)
+        w["tiles_ok"] = n_cap >= 2048 and BeamTiles.supported(plan.beams[:min(nbm, 6)]) and \
+            (nbm <= 6 or all(BeamTiles.supported([plan.beams[0], b]) for b in plan.beams[6:])) and \
+            (plan.basis is None or 4 * (plan.basis["K"] * (plan.basis["K"] + 1) // 2) <= 64)
+        if w["tiles_ok"]:
+            with torch.cuda.device(dev):
+                w["tiles"] = BeamTiles()
         if plan.basis is not None:
             npairs = plan.basis["K"] * (plan.basis["K"] + 1) // 2
             if 4 * npairs <= 64:                        # K <= 5: all pairs as one batched transform
@@ -473,7 +512,7 @@ class GPUSimulationEngine(SimulationEngine):
                     lo, hi = ch * chunk, min(plan.nsrc, (ch + 1) * chunk)
                     if lo >= hi:
                         continue
-                    _lib.check(L.fv_rotate_cut(
+                    _lib.check(self._timed("rotate_cut", st, L.fv_rotate_cut,
                         prec, plan.eq_xyz.data_ptr(), plan.nsrc, lo, hi,
                         _lib.doubles(plan.enu_mats[ti].ravel()),
                         _lib.doubles(plan.astrom[ti]) if plan.astrom is not None else None,
@@ -482,6 +521,13 @@ class GPUSimulationEngine(SimulationEngine):
                         w["src_idx"].data_ptr(), plan.n_cap, w["n_dev"].data_ptr(),
                         w["scratch"].data_ptr(), st.cuda_stream), "fv_rotate_cut")
                     w["counts"][ti, ch:ch + 1].copy_(w["n_dev"])
+                    tiles = None
+                    if self.beam_tiles and w.get("tiles_ok"):
+                        tiles = w["tiles"]
+                        self._timed("tile_sort", st, tiles.sort, prec, plan.beams[0], w["xyz"], w["az"], w["za"],
+                                    w["src_idx"], w["n_dev"], plan.n_cap)
+                        if self.beam_tiles == "sort":        # sorted live set, taps gathered from global memory
+                            tiles = None
                     xlim = None
                     if not plan.use_type1:
                         import ctypes
@@ -498,12 +544,19 @@ class GPUSimulationEngine(SimulationEngine):
                         obase = out.data_ptr() + ((f0 - plan.f_lo) * s_f + to * s_t) * esz
                         sb_, sp_ = s_f, plan.nbls
                         if plan.basis is not None:
-                            self._basis_batch(plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st)
+                            self._basis_batch(plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st,
+                                              tiles=tiles)
                             continue
                         for pt in plan.pairs:
-                            launch_weights(prec, mode, plan.beams[pt.bi], plan.beams[pt.bj], w["az"], w["za"],
-                                           w["src_idx"], w["n_dev"], plan.n_cap, plan.freqs_dev, f0, nb,
-                                           plan.flux, plan.nsrc, w["W"], None, st)
+                            if tiles is not None:
+                                bb = [plan.beams[pt.bi]] if pt.bi == pt.bj else [plan.beams[pt.bi], plan.beams[pt.bj]]
+                                self._timed("weights", st, tiles.weights, prec, mode, bb, False, w["az"], w["za"],
+                                            w["src_idx"], plan.n_cap, plan.freqs_dev, f0, nb, plan.flux, plan.nsrc,
+                                            w["W"])
+                            else:
+                                self._timed("weights", st, launch_weights, prec, mode, plan.beams[pt.bi],
+                                            plan.beams[pt.bj], w["az"], w["za"], w["src_idx"], w["n_dev"], plan.n_cap,
+                                            plan.freqs_dev, f0, nb, plan.flux, plan.nsrc, w["W"], None, st)
                             epi = _lib.make_epilogue(
                                 obase, sb_, sp_, pmap, pt.kmap.data_ptr() if pt.kmap is not None else 0,
                                 pt.conj.data_ptr() if pt.conj is not None else 0, accumulate=True)
@@ -540,7 +593,7 @@ class GPUSimulationEngine(SimulationEngine):
             nufft.type3(plan.precision, dim, w["xyz"], w["n_dev"], xlim, pt.uvw, pt.ulim, scale, W,
                         plan.eps, plan.upsample_factor, epi)
 
-    def _basis_batch(self, plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st):
+    def _basis_batch(self, plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st, tiles=None):
         """K (K + 1) / 2 transforms over all baselines + contraction (cpu_simulate.py:416-468): every basis
         beam is evaluated once per (source, frequency) (``fv_weights_basis``), the pair products are the
         strengths of ONE batched transform with 4 K (K + 1) / 2 components on the fused type-1 path (the
@@ -554,8 +607,12 @@ class GPUSimulationEngine(SimulationEngine):
         if "Wb" not in w:
             return self._basis_batch_pairs(plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st)
         Wb, vkl = w["Wb"][:nb], w["vkl"]
-        launch_weights_basis(plan.precision, mode, plan.beams[:K], w["az"], w["za"], w["src_idx"], w["n_dev"],
-                             plan.n_cap, plan.freqs_dev, f0, nb, plan.flux, plan.nsrc, Wb, st)
+        if tiles is not None:
+            self._timed("weights", st, tiles.weights, plan.precision, mode, plan.beams[:K], True, w["az"], w["za"],
+                        w["src_idx"], plan.n_cap, plan.freqs_dev, f0, nb, plan.flux, plan.nsrc, Wb)
+        else:
+            self._timed("weights", st, launch_weights_basis, plan.precision, mode, plan.beams[:K], w["az"], w["za"],
+                        w["src_idx"], w["n_dev"], plan.n_cap, plan.freqs_dev, f0, nb, plan.flux, plan.nsrc, Wb, st)
         if plan.use_type1 and self.type1_method == "fused":
             epi = _lib.make_epilogue(vkl.data_ptr(), vkl.stride(0), vkl.stride(1), _FEED_SWAP)
             self._nufft_batch(plan, w, nufft, pt, dim, xlim, scale, nb, epi, W=Wb)

@@ -133,6 +133,27 @@ int fv_weights_basis(int prec, int mode, const fv_beam* beams_host, int K, const
                      const int32_t* src_idx, const int32_t* n_dev, int64_t n_cap, const double* freqs, int nf,
                      int64_t freq_index0, const void* flux, int64_t nsrc_total, void* out, void* stream);
 
+/* ---- az/za table beams staged in shared memory (north_star (2): "the beam grid staged in shared memory,
+ * TMA where it tiles"; same arithmetic as fv_weights / fv_weights_basis for table beams of order 0 / 1,
+ * i.e. pyuvdata's az/za interpolation behind evaluate_beam, cpu/beams.py:12-89).
+ * fv_tiles_sort: once per (time step, source chunk), after fv_rotate_cut: sorts the live set by the 16 x 16-cell
+ *   tile of the beam grid each direction falls in and re-orders xyz / az / za / src_idx IN PLACE (stable: slots of
+ *   a tile keep their catalogue order), so that slot == sorted position for everything downstream.
+ * fv_weights_tiled: one CTA per (tile, group of frequencies) copies the tile's 17 x 17-point patch of every Jones
+ *   entry into shared memory (cp.async.bulk rows + mbarrier, double-buffered over the frequencies) and evaluates
+ *   all of the tile's sources from it.  basis = 0: the pair (beams[0], beams[K-1]), K = 1 or 2, out as fv_weights;
+ *   basis = 1: all pairs k <= l of the K <= 6 beams, out as fv_weights_basis.
+ * fv_tiles_supported: 1 when the K beams are tables of order 0 / 1 on one common grid. */
+typedef struct fv_tiles fv_tiles;
+int fv_tiles_create(fv_tiles** tiles, void* stream);
+int fv_tiles_destroy(fv_tiles* tiles);
+int fv_tiles_supported(const fv_beam* beams_host, int K);
+int fv_tiles_sort(fv_tiles* tiles, int prec, const fv_beam* beam_host, void* xyz /* (3, n_cap) */, void* az, void* za,
+                  int32_t* src_idx, const int32_t* n_dev, int64_t n_cap);
+int fv_weights_tiled(fv_tiles* tiles, int prec, int mode, const fv_beam* beams_host, int K, int basis,
+                     const void* az, const void* za, const int32_t* src_idx, int64_t n_cap, const double* freqs,
+                     int nf, int64_t freq_index0, const void* flux, int64_t nsrc_total, void* out);
+
 /* stand-alone apparent-coherency products on caller-supplied beam values: the four methods of
  * CPUBeamEvaluator (cpu/beams.py:129-246).  mode 1: A_i^H diag(F) A_j; mode 4: A_i^H C A_j;
  * mode 2: as 4 with both beams flipped along the vector axis (cpu_simulate.py:146-147,153).
