@@ -14,6 +14,8 @@ from typing import Any, Dict, Tuple
 
 import numpy as np
 
+from .utils import memo_by_value as _memo
+
 
 def find_integer_multiplier(arr: np.ndarray, max_denominator: int = 10**6) -> int:
     """Least common denominator of the (rationalised) non-zero entries of ``arr``
@@ -54,6 +56,7 @@ def find_lattice_basis(antpos: Dict[Any, np.ndarray], tol: float = 1e-9):
     return np.column_stack([b1, sep[1 + hits[0]]])
 
 
+@_memo()
 def check_antpos_griddability(antpos: Dict[Any, np.ndarray], tol: float = 1e-9,
                               max_denominator: int = 10**6, max_factor: int = 1000):
     """(is_griddable, integer antenna coords, 3x3 basis/factor) -- reference

@@ -18,6 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import astrometry
+from .utils import memo_by_value
 
 TWO_PI = 2.0 * np.pi
 
@@ -93,6 +94,10 @@ def earth_rotation_angle(jd_ut1: np.ndarray) -> np.ndarray:
     return astrometry.earth_rotation_angle(jd_ut1)
 
 
+# the per-time blocks depend on (times, site, IERS parameters) only: memoised on those values
+_astrom_blocks = memo_by_value()(astrometry.astrom_blocks)
+
+
 def coordinate_blocks(times, telescope_loc, coord_method: str = "CoordinateRotationERFA",
                       coord_method_params: dict | None = None) -> tuple[np.ndarray, np.ndarray | None]:
     """Per-time blocks ``(enu_mats (nt, 3, 3), astrom (nt, 10) or None)`` handed to ``fv_rotate_cut``.
@@ -114,7 +119,7 @@ def coordinate_blocks(times, telescope_loc, coord_method: str = "CoordinateRotat
         ast = params.get("astrom")
         return mats, (None if ast is None else np.ascontiguousarray(ast, dtype=np.float64).reshape(len(mats), 10))
     lat, lon = site_lat_lon(telescope_loc)
-    blk = astrometry.astrom_blocks(
+    blk = _astrom_blocks(
         times_to_jd(times), lat, lon, site_height(telescope_loc), dut1=float(params.get("dut1", 0.0)),
         xp=float(params.get("xp", 0.0)), yp=float(params.get("yp", 0.0)),
         update_bcrs_every=float(params.get("update_bcrs_every", 0.0)),

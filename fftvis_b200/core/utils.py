@@ -17,6 +17,50 @@ logger = logging.getLogger(__name__)
 speed_of_light = 299792458.0  # m/s, reference core/utils.py:9
 
 
+def memo_by_value(maxsize: int = 4):
+    """Memoise a pure host planner on the VALUES of its arguments (antenna-position dicts and arrays are keyed
+    by their bytes).  An array layout or a set of observation times is a property of the instrument, not of
+    one ``simulate`` call: repeated calls with the same layout skip the O(N_ant^2) planning, a different
+    layout recomputes.  Results are returned as deep copies, so callers may modify them."""
+    import copy
+    import functools
+
+    def key_of(v):
+        if isinstance(v, dict):
+            return ("d", tuple(v.keys()), tuple(np.asarray(x, dtype=float).tobytes() for x in v.values()))
+        if isinstance(v, np.ndarray):
+            return ("a", v.dtype.str, v.shape, v.tobytes())
+        if isinstance(v, (list, tuple)):
+            return ("l", tuple(key_of(x) for x in v))
+        return v
+
+    def _fresh(r):
+        # lists of (lists of) immutable tuples: new list objects; anything else: a deep copy
+        if isinstance(r, list) and all(isinstance(g, (tuple, list)) for g in r):
+            return [list(g) if isinstance(g, list) else g for g in r]
+        return copy.deepcopy(r)
+
+    def deco(fn):
+        cache = {}
+
+        @functools.wraps(fn)
+        def wrapped(*args, **kwargs):
+            try:
+                key = (tuple(key_of(a) for a in args), tuple(sorted((k, key_of(v)) for k, v in kwargs.items())))
+                hash(key)
+            except TypeError:
+                return fn(*args, **kwargs)
+            if key not in cache:
+                if len(cache) >= maxsize:
+                    cache.pop(next(iter(cache)))
+                cache[key] = fn(*args, **kwargs)
+            return _fresh(cache[key])
+
+        wrapped.cache_clear = cache.clear
+        return wrapped
+    return deco
+
+
 def _pair_table(antpos: dict, include_autos: bool):
     """All (i<j [, i==j]) antenna pairs in the dict's iteration order (outer i, inner j)."""
     keys = list(antpos.keys())
@@ -29,6 +73,7 @@ def _pair_table(antpos: dict, include_autos: bool):
     return keys, pos, ii[sel], jj[sel]
 
 
+@memo_by_value()
 def get_pos_reds(antpos, decimals=3, include_autos=True, representatives_only=False):
     """Redundant-baseline groups from antenna positions (reference core/utils.py:11-71).
 

@@ -227,6 +227,7 @@ extern "C" int fv_plan_set_option(fv_plan* P, const char* name, int64_t value) {
   else if (n == "t3_tiles") P->t3_tiles = (int)value;
   else if (n == "t1_small") P->t1_small = (int)value;
   else if (n == "t1_xdirect") P->t1_xdirect = (int)value;
+  else if (n == "timing_mask") P->timing_mask = (int)value;
   else if (n == "t3_fft") P->t3_fft = (int)value;
   else if (n.rfind("t3_v", 0) == 0 && n.size() == 5 && n[4] >= 'x' && n[4] <= 'z') P->t3_v[n[4] - 'x'] = (int)value;
   else if (n.rfind("t3_thr", 0) == 0 && n.size() == 7 && n[6] >= 'x' && n[6] <= 'z') P->t3_thr[n[6] - 'x'] = (int)value;

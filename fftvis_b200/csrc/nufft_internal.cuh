@@ -494,6 +494,7 @@ struct fv_plan {
   size_t fft_work_bytes = 0;
   size_t table_bytes = 0;
   bool timing = false;                       // CUDA events around every stage launch
+  int timing_mask = (1 << FV_STAGE_COUNT) - 1; // ... of the stages whose bit is set (option "timing_mask")
   double stage_ms[FV_STAGE_COUNT] = {0};
   int64_t stage_n[FV_STAGE_COUNT] = {0};
   struct Pending { int stage; cudaEvent_t e0, e1; };
@@ -600,7 +601,7 @@ struct StageScope {
     cudaEvent_t e; cudaEventCreate(&e); return e;
   }
   StageScope(fv_plan* P_, int stage_) : P(P_), stage(stage_) {
-    if (P->timing) { e0 = get(P); e1 = get(P); cudaEventRecord(e0, P->stream); }
+    if (P->timing && ((P->timing_mask >> stage_) & 1)) { e0 = get(P); e1 = get(P); cudaEventRecord(e0, P->stream); }
   }
   ~StageScope() {
     if (e0) { cudaEventRecord(e1, P->stream); P->pending.push_back({stage, e0, e1}); }
