@@ -56,3 +56,11 @@ def test_product_never_imports_the_oracle():
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), path
     for path in (ROOT / "fftvis_b200" / "csrc").glob("*.cu*"):
         assert "oracle/" not in path.read_text(), path
+
+
+def test_oracle_never_imports_the_product():
+    """The checker stands on its own: no module under oracle/ imports fftvis_b200 (beam containers and synthetic
+    workloads reach it as arguments, duck-typed)."""
+    for path in (ROOT / "oracle").glob("*.py"):
+        src = path.read_text()
+        assert not re.search(r"^\s*(from|import)\s+fftvis_b200\b", src, flags=re.M), path
