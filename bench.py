@@ -516,7 +516,8 @@ def build_roofline(args, eng, plan2, stages, n_live, hbm_peak, peak_src, w, nf_l
         tf = ROOT / "profiles" / "r02_traffic.json"
         if tf.exists() and eng.type1_method == "fused":
             prof = json.loads(tf.read_text())
-            traffic = prof.get(w["name"], {}).get("pass1")
+            per_f = prof.get(w["name"], {}).get("pass1_bytes_per_transform")     # ncu dram read + write / transforms
+            traffic = None if per_f is None else per_f * nb_mean
             on_chip = prof.get(w["name"] + "_ncu")        # ncu: issue-active and shared-memory pipe utilisation
         return {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                 "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
