@@ -81,7 +81,7 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   if (rc) return rc;
   const int ncols = tab->ncols;
   const int pitch = (int)nf + 1;
-  const size_t tneed = sizeof(C) * (size_t)nb * ntr * ncols * nf;
+  const size_t tneed = sizeof(C) * (size_t)nb * ntr * (8 * (size_t)((ncols + 7) / 8)) * nf;   // blocks of 8 columns (x-direct)
   rc = ensure(&P->tbuf, &P->tbuf_bytes, tneed);
   if (rc) return rc;
   std::vector<BatchParams> bp(nb);

@@ -702,7 +702,7 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
 
 template <typename T>
 struct T1GatherArgs {
-  const cplx_t<T>* Tbuf;         // (nb, ntr, ncols, nf); (nb, ntr, nf, ncols) when t_rowmajor (x-direct pass 1)
+  const cplx_t<T>* Tbuf;         // (nb, ntr, ncols, nf); (nb, ntr, ceil(ncols / 8), nf, 8) when t_rowmajor (x-direct pass 1)
   int nf, pitch, ncols, cols_per_cta, ntr, t_rowmajor;
   const cplx_t<T>* tw;
   FftStages st;
@@ -729,13 +729,37 @@ t1_ffty_gather_kernel(T1GatherArgs<T> a) {
   // columns -> shared memory with asynchronous copies (LDGSTS): every element's load is in flight
   // at once instead of a register round trip per element
   if (a.t_rowmajor) {
-    // rows of nc consecutive columns: element i -> (row i / nc, column i % nc)
-    const C* Tr = a.Tbuf + (int64_t)bpi * a.ncols * nf + c0;
-    const unsigned inv_nc = nc > 1 ? 0xFFFFFFFFu / (unsigned)nc + 1u : 0u;
-    for (int i = tid; i < nc * nf; i += blockDim.x) {
-      const int rr = inv_nc ? (int)__umulhi((unsigned)i, inv_nc) : i;
-      const int ci = i - rr * nc;
-      __pipeline_memcpy_async(cols + ci * pitch + rr, Tr + (int64_t)rr * a.ncols + ci, sizeof(C));
+    // x-direct pass 1 writes T in blocks of 8 columns: [column group][row][8 columns], so a CTA's columns are whole
+    // contiguous blocks of nf x 8 entries.  16-byte loads (two columns of one row), five in flight per thread,
+    // then one 8-byte shared-memory store per column: the transpose to column vectors happens on the way in.
+    const int ncg = (a.ncols + 7) >> 3;
+    if (sizeof(C) == 8 && (c0 & 7) == 0) {
+      for (int g = 0; g * 8 < nc; ++g) {
+        const float4* blk = reinterpret_cast<const float4*>(a.Tbuf) + ((int64_t)bpi * ncg + (c0 >> 3) + g) * nf * 4;
+        float2* cg = reinterpret_cast<float2*>(cols) + (size_t)g * 8 * pitch;
+        const int ncg_cols = min(8, nc - g * 8);
+        const int tot = nf * 4;
+        for (int i0 = tid; i0 < tot; i0 += 5 * blockDim.x) {
+          float4 v[5];
+#pragma unroll
+          for (int u = 0; u < 5; ++u) { const int i = i0 + u * blockDim.x; if (i < tot) v[u] = blk[i]; }
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < tot) {
+              const int rr = i >> 2, cc = (i & 3) * 2;
+              if (cc < ncg_cols) cg[cc * pitch + rr] = make_float2(v[u].x, v[u].y);
+              if (cc + 1 < ncg_cols) cg[(cc + 1) * pitch + rr] = make_float2(v[u].z, v[u].w);
+            }
+          }
+        }
+      }
+    } else {
+      for (int i = tid; i < nc * nf; i += blockDim.x) {
+        const int ci = i / nf, rr = i - ci * nf, cgl = c0 + ci;
+        __pipeline_memcpy_async(cols + ci * pitch + rr,
+                                a.Tbuf + (((int64_t)bpi * ncg + (cgl >> 3)) * nf + rr) * 8 + (cgl & 7), sizeof(C));
+      }
     }
   } else {
     for (int ci = tid >> 5; ci < nc; ci += blockDim.x >> 5) {

@@ -1,7 +1,7 @@
 // Pass 1 of the fused type-1 path without an x grid ("x-direct"), single precision.
 //
 // The half-transformed array the y pass needs is
-//     T[row][col] = sum_s  W_s * phi_y(row - y_s) * exp(+i k_col x_s)          k_col = first mode number of column col
+//     T[col][row] = sum_s  W_s * phi_y(row - y_s) * exp(+i k_col x_s)          k_col = first mode number of column col
 // i.e. gridded in y (exponential-of-semicircle kernel, as in finufft.nufft2d1, reference cpu/nufft.py:120-175) but an
 // exact Fourier sum in x: only n_cols <= n_modes of the nf columns are ever read by a baseline, so spreading w cells
 // in x, transforming nf-point rows and discarding most outputs costs more than evaluating the n_cols phases
@@ -17,8 +17,8 @@
 //                       (the hit records of a chunk are sorted by first row, so each first row is its own branch-free
 //                       loop): no shared-memory grid, no atomics, no FFT, no barrier inside the hit loops.
 //
-// The y pass (t1_ffty_gather_kernel) then divides by the kernel transform in y only.  T is row-major here (a warp
-// stores 32 consecutive columns of one row: 256 contiguous bytes).
+// The y pass (t1_ffty_gather_kernel) then divides by the kernel transform in y only.  T is stored in blocks of 8
+// columns, [column group][row][8]: a warp stores four 64-byte runs per row and the y pass reads whole blocks.
 //
 // Error model: x is exact up to the phase rounding (2^-32 turn * |k| + the sin/cos approximation, ~4e-7 absolute),
 // y is the finufft kernel at the requested width: never worse than the two-dimensional spreader it replaces.
@@ -195,7 +195,7 @@ struct T1XdArgs {
   const int32_t* strip_off; const int32_t* list; int64_t lcap;
   int ncols;
   const int32_t* col_k;          // signed first mode number of every needed column
-  float2* Tbuf;                  // (nb, ntr, nf, ncols)
+  float2* Tbuf;                  // (nb, ntr, ceil(ncols / 8), nf, 8)
 };
 
 // acc[c - (W - 1) + j] += ky[j] * p for the rows of the footprint that fall inside the strip
@@ -342,9 +342,12 @@ t1_xdirect_kernel(T1XdArgs a) {
   }
 
   if (col < a.ncols) {
-    float2* Tb = a.Tbuf + ((int64_t)bpi * nf + r0) * a.ncols + col;
+    // T in blocks of 8 columns, [column group][row][8]: a warp stores four 64-byte runs per row, and pass 2 reads
+    // its 8 columns as one contiguous block
+    const int ncg = (a.ncols + 7) >> 3;
+    float2* Tb = a.Tbuf + (((int64_t)bpi * ncg + (col >> 3)) * nf + r0) * 8 + (col & 7);
 #pragma unroll
-    for (int r = 0; r < R; ++r) if (r < rows) Tb[(int64_t)r * a.ncols] = acc[r];
+    for (int r = 0; r < R; ++r) if (r < rows) Tb[r * 8] = acc[r];
   }
 }
 
