@@ -221,6 +221,19 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   g.tw = (const C*)F->tw; g.st = F->st; g.col_off = tab->col_off; g.s_k = tab->s_k; g.s_pos = tab->s_pos;
   g.s_scale = (const T*)(use_xd ? tab->s_scale_y : tab->s_scale); g.epi = make_epi(epi);
   g.t_rowmajor = use_xd ? 1 : 0;
+  // blocked T (x-direct pass 1): one CTA per block of 8 columns, transformed in the block's own layout
+  const size_t smem8 = sizeof(float2) * (size_t)nf * 9;       // the block + twiddles
+  if (use_xd && P->t1_cols == 0 && smem8 <= 74 * 1024) {
+    if constexpr (sizeof(T) == 4) {
+      StageScope ts(P, FV_STAGE_GATHER);
+      auto kern8 = t1_ffty8_gather_kernel<T>;
+      FV_CUDA(cudaFuncSetAttribute(kern8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      dim3 grid(ceil_div(ncols, 8), nb * ntr);
+      kern8<<<grid, T1_THREADS, smem8, P->stream>>>(g);
+      FV_LAUNCH_CHECK();
+      return FV_OK;
+    }
+  }
   {
     StageScope ts(P, FV_STAGE_GATHER);
     auto kern = t1_ffty_gather_kernel<T>;

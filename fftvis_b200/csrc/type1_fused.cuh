@@ -787,4 +787,90 @@ t1_ffty_gather_kernel(T1GatherArgs<T> a) {
   }
 }
 
+// ---- pass 2 on the blocked T of the x-direct pass 1 (single precision) --------------------------------------------
+// One CTA per block of 8 columns.  The block ([row][8 columns], nf x 64 bytes, contiguous) comes in by bulk copies
+// (TMA, cp.async.bulk + mbarrier) and is transformed IN that layout: a lane is (column, butterfly), so the 32 lanes of
+// every shared-memory access cover 4 rows x 8 columns = 256 contiguous bytes, and no transpose or padding is needed.
+// All warps share the 8 columns, so the stages are separated by CTA barriers.
+template <int R>
+__device__ __forceinline__ void fft_stage_il(float2* d, int N, int n, unsigned inv, const float2* __restrict__ tws,
+                                             int tid, int nthr) {
+  const int m = n / R, per_vec = N / R;
+  const int col = tid & 7;
+  for (int t = tid >> 3; t < per_vec; t += nthr >> 3) {
+    const int blk = inv ? (int)__umulhi((unsigned)t, inv) : t;
+    const int j = t - blk * m;
+    float2* p = d + (blk * n + j) * 8 + col;
+    float2 x[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) x[q] = p[q * m * 8];
+    dft_r<float, R>(x);
+    p[0] = x[0];
+    if (m > 1) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) p[q * m * 8] = cmul(x[q], tws[(q - 1) * m + j]);
+    } else {
+#pragma unroll
+      for (int q = 1; q < R; ++q) p[q * 8] = x[q];
+    }
+  }
+}
+
+template <typename T>                                     // T = float only (a template so that every translation unit may include it)
+__global__ void __launch_bounds__(T1_THREADS, 3)
+t1_ffty8_gather_kernel(T1GatherArgs<T> a) {
+  static_assert(sizeof(T) == 4, "single precision");
+  using C = float2;
+  extern __shared__ __align__(128) unsigned char t1_smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  C* blk = (C*)t1_smem;                                     // [nf][8]
+  C* tw = blk + (size_t)a.nf * 8;                           // twiddles
+  const int nf = a.nf;
+  const int bpi = blockIdx.y, b = bpi / a.ntr, p = bpi - b * a.ntr;
+  const int c0 = blockIdx.x * 8;
+  const int nc = min(8, a.ncols - c0);
+  const int tid = threadIdx.x;
+  const int ncg = (a.ncols + 7) >> 3;
+  const unsigned bar_a = smem_u32(&bar);
+  if (tid == 0) mbar_init(bar_a, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) {
+    // the block in runs of at most 16 KB, one per lane
+    const unsigned total = (unsigned)nf * 64u;
+    const char* src = reinterpret_cast<const char*>(a.Tbuf) + ((int64_t)bpi * ncg + blockIdx.x) * (int64_t)total;
+    if (tid == 0) mbar_expect_tx(bar_a, total);
+    __syncwarp();
+    for (unsigned off = (unsigned)tid * 16384u; off < total; off += 32u * 16384u)
+      bulk_g2s(smem_u32(blk) + off, src + off, min(16384u, total - off), bar_a);
+  }
+  for (int i = tid; i < a.st.tw_len; i += blockDim.x) tw[i] = a.tw[i];
+  const int k0 = a.col_off[c0], k1 = a.col_off[c0 + nc];
+  mbar_wait(bar_a, 0u);
+  __syncthreads();
+  int n = nf;
+  for (int s = 0; s < a.st.nstage; ++s) {
+    const unsigned inv = a.st.inv_m[s];
+    const C* tws = tw + a.st.tw_off[s];
+    switch (a.st.radix[s]) {
+      case 15: fft_stage_il<15>(blk, nf, n, inv, tws, tid, blockDim.x); n /= 15; break;
+      case 8: fft_stage_il<8>(blk, nf, n, inv, tws, tid, blockDim.x); n /= 8; break;
+      case 4: fft_stage_il<4>(blk, nf, n, inv, tws, tid, blockDim.x); n /= 4; break;
+      case 2: fft_stage_il<2>(blk, nf, n, inv, tws, tid, blockDim.x); n /= 2; break;
+      case 5: fft_stage_il<5>(blk, nf, n, inv, tws, tid, blockDim.x); n /= 5; break;
+      default: fft_stage_il<3>(blk, nf, n, inv, tws, tid, blockDim.x); n /= 3; break;
+    }
+    __syncthreads();
+  }
+  // walk the column-sorted baselines of this CTA's columns
+  for (int kk = k0 + tid; kk < k1; kk += blockDim.x) {
+    int lo = 0, hi = nc;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.col_off[c0 + mid] <= kk) lo = mid; else hi = mid; }
+    C v = blk[a.s_pos[kk] * 8 + lo];
+    const float sc = a.s_scale[kk];
+    v.x *= sc; v.y *= sc;
+    epilogue_store(a.epi, b, p, (int64_t)a.s_k[kk], v);
+  }
+}
+
 }  // namespace fv
