@@ -750,7 +750,8 @@ static int get_smem_fft(fv_plan* P, int prec, int64_t nf, fv_plan::SmemFft** out
     if (prec == 1) ((float2*)host.data())[t] = make_float2((float)twr[t], (float)twi[t]);
     else ((double2*)host.data())[t] = make_double2(twr[t], twi[t]);
   }
-  FV_CUDA(cudaMalloc(&f.tw, host.size()));
+  FV_CUDA(cudaMalloc(&f.tw, host.size() + 16));      // + 16: bulk copies of the table round its size up to 16 bytes
+  FV_CUDA(cudaMemsetAsync(f.tw, 0, host.size() + 16, P->stream));
   FV_CUDA(cudaMemcpyAsync(f.tw, host.data(), host.size(), cudaMemcpyHostToDevice, P->stream));
   FV_CUDA(cudaStreamSynchronize(P->stream));
   P->table_bytes += host.size();

@@ -838,13 +838,14 @@ t1_ffty8_gather_kernel(T1GatherArgs<T> a) {
   if (tid < 32) {
     // the block in runs of at most 16 KB, one per lane
     const unsigned total = (unsigned)nf * 64u;
+    const unsigned tw_bytes = ((unsigned)a.st.tw_len * 8u + 15u) & ~15u;     // the table is allocated with 16 bytes to spare
     const char* src = reinterpret_cast<const char*>(a.Tbuf) + ((int64_t)bpi * ncg + blockIdx.x) * (int64_t)total;
-    if (tid == 0) mbar_expect_tx(bar_a, total);
+    if (tid == 0) mbar_expect_tx(bar_a, total + tw_bytes);
     __syncwarp();
     for (unsigned off = (unsigned)tid * 16384u; off < total; off += 32u * 16384u)
       bulk_g2s(smem_u32(blk) + off, src + off, min(16384u, total - off), bar_a);
+    if (tid == 31) bulk_g2s(smem_u32(tw), a.tw, tw_bytes, bar_a);
   }
-  for (int i = tid; i < a.st.tw_len; i += blockDim.x) tw[i] = a.tw[i];
   const int k0 = a.col_off[c0], k1 = a.col_off[c0 + nc];
   mbar_wait(bar_a, 0u);
   __syncthreads();

@@ -559,7 +559,10 @@ class GPUSimulationEngine(SimulationEngine):
                                             plan.freqs_dev, f0, nb, plan.flux, plan.nsrc, w["W"], None, st)
                             epi = _lib.make_epilogue(
                                 obase, sb_, sp_, pmap, pt.kmap.data_ptr() if pt.kmap is not None else 0,
-                                pt.conj.data_ptr() if pt.conj is not None else 0, accumulate=True)
+                                pt.conj.data_ptr() if pt.conj is not None else 0,
+                                # every baseline belongs to exactly one beam pair and `out` starts at zero: only the
+                                # later source chunks add to what is there (cpu_simulate.py:1069 `vis[...] +=`)
+                                accumulate=ch > 0)
                             self._nufft_batch(plan, w, nufft, pt, dim, xlim, scale, nb, epi)
                 if copy_st is not None:
                     self._stream_slab(out, host_out, to, st, copy_st)
