@@ -288,6 +288,7 @@ def run_gpu(args):
     beam = w["beam"] if w["polarized"] else w["beam"].to_power()
     beam_list = beam if isinstance(beam, list) else [beam]
     eng = GPUSimulationEngine(freq_batch=args.freq_batch, type1_method=args.type1_method)
+    eng.two_streams = not args.one_stream
     if args.no_beam_tiles:
         eng.beam_tiles = False
     elif os.environ.get("FV_BEAM_TILES"):                    # "sort" (default) or "smem"
@@ -324,9 +325,20 @@ def run_gpu(args):
     # gather, weights, rotate ...) would add ~9 k event records per cfg2 step to the timed region, so their
     # breakdown comes from ONE extra step after it (``stages_from``).
     dominant = (1 << 1) if plan.use_type1 else ((1 << 1) | (1 << 2) | (1 << 4))
-    nufft.set_option("timing_mask", dominant)
-    nufft.set_timing(True)
-    nufft.reset_timing()
+    plans = eng.nufft_plans(plan.device)                 # main stream + the side stream of alternate batches
+
+    def merged_stage_times():
+        tot = {}
+        for pl in plans:
+            for k, (ms_, n_) in pl.stage_times().items():
+                a_, b_ = tot.get(k, (0.0, 0))
+                tot[k] = (a_ + ms_, b_ + n_)
+        return tot
+
+    for pl in plans:
+        pl.set_option("timing_mask", dominant)
+        pl.set_timing(True)
+        pl.reset_timing()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -341,10 +353,11 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     launches = _lib.lib().fv_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    stages = nufft.stage_times()
+    stages = merged_stage_times()
     # one extra step with every stage timed
-    nufft.set_option("timing_mask", (1 << 6) - 1)
-    nufft.reset_timing()
+    for pl in plans:
+        pl.set_option("timing_mask", (1 << 6) - 1)
+        pl.reset_timing()
     eng.time_stages = True
     eng.stage_times()
     xe0, xe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -354,10 +367,11 @@ def run_gpu(args):
     xe1.record()
     barrier()
     extra_ms = xe0.elapsed_time(xe1)
-    stages_all = nufft.stage_times()
+    stages_all = merged_stage_times()
     stages_all.update(eng.stage_times())                 # rotate + cut, beam-tile sort, weights
     eng.time_stages = False
-    nufft.set_timing(False)
+    for pl in plans:
+        pl.set_timing(False)
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -572,6 +586,7 @@ def main():
                     help="type-3 transforms even for a gridded array (the reference's force_use_type3)")
     ap.add_argument("--no-beam-tiles", action="store_true",
                     help="table beams gathered from global memory instead of staged in shared memory")
+    ap.add_argument("--one-stream", action="store_true", help="no side stream for alternate frequency batches")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffers) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -115,6 +115,18 @@ def _copy_stream(dev) -> torch.cuda.Stream:
     return _COPY_STREAMS[key]
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(dev) -> torch.cuda.Stream:
+    """One side compute stream per device: alternate frequency batches of the fused type-1 path run on it, so
+    that the tail of one batch's kernels overlaps the head of the next batch's."""
+    key = torch.device(dev).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 def _next235even(n: int) -> int:
     return int(_lib.lib().fv_next235even(int(n)))
 
@@ -141,6 +153,10 @@ class GPUSimulationEngine(SimulationEngine):
         # events around every launch while ``time_stages`` is set (bench.py); read with ``stage_times()``
         self.time_stages = False
         self._stage_events = []
+        # fused type-1 path: odd frequency batches on a side stream with their own strengths / work buffers
+        # (the kernels of consecutive batches then overlap: pass 2's latency-bound waves and the wave tails of
+        # pass 1 fill with the other batch's CTAs); False = one stream
+        self.two_streams = True
 
     # ------------------------------------------------------------------------------------------
     def _timed(self, name, st, fn, *a, **k):
@@ -169,6 +185,15 @@ class GPUSimulationEngine(SimulationEngine):
         if self.device is not None:
             return torch.device(self.device)
         return torch.device("cuda", torch.cuda.current_device())
+
+    def nufft_plans(self, dev) -> list:
+        """Every NUFFT plan ``run_plan`` launches on: the current stream's and, with ``two_streams``, the side
+        stream's (for callers that switch the per-stage timers on and read them: bench.py)."""
+        plans = [self._nufft_plan(dev)]
+        if self.two_streams:
+            with torch.cuda.device(dev), torch.cuda.stream(_side_stream(dev)):
+                plans.append(default_plan())
+        return plans
 
     def _nufft_plan(self, dev) -> NufftPlan:
         """The process-wide plan of (device, current stream): its work areas and twiddle tables outlive
@@ -507,6 +532,15 @@ class GPUSimulationEngine(SimulationEngine):
                 copy_st = _copy_stream(dev)
                 copy_st.wait_stream(st)                      # the zero fill precedes every slab copy
             s_f, s_t = out.stride(0), out.stride(1)          # in elements
+            two = bool(self.two_streams and plan.use_type1 and self.type1_method == "fused" and plan.basis is None
+                       and plan.nf_local > plan.freq_batch)
+            if two:
+                side = _side_stream(dev)
+                with torch.cuda.stream(side):
+                    nufft2 = default_plan()                   # the side stream's own plan (work buffers, T)
+                if "W2" not in w:
+                    w["W2"] = torch.empty_like(w["W"])
+                ev_rc = torch.cuda.Event()
             for to, ti in enumerate(range(t_lo, t_hi)):
                 for ch in range(plan.nchunks):
                     lo, hi = ch * chunk, min(plan.nsrc, (ch + 1) * chunk)
@@ -538,11 +572,25 @@ class GPUSimulationEngine(SimulationEngine):
                         xlim = [lim[i] for i in range(2 * dim)]
                         if not (xlim[0] <= xlim[1]):
                             continue                         # nothing above the horizon
-                    for f0 in range(plan.f_lo, plan.f_hi, plan.freq_batch):
+                    if two:
+                        ev_rc.record(st)
+                        side.wait_event(ev_rc)               # the live set of this (time, chunk) is ready
+                    for jb, f0 in enumerate(range(plan.f_lo, plan.f_hi, plan.freq_batch)):
                         nb = min(plan.freq_batch, plan.f_hi - f0)
                         scale = freqs64[f0:f0 + nb]
                         obase = out.data_ptr() + ((f0 - plan.f_lo) * s_f + to * s_t) * esz
                         sb_, sp_ = s_f, plan.nbls
+                        if two and (jb & 1) and tiles is None:
+                            for pt in plan.pairs:
+                                self._timed("weights", side, launch_weights, prec, mode, plan.beams[pt.bi],
+                                            plan.beams[pt.bj], w["az"], w["za"], w["src_idx"], w["n_dev"], plan.n_cap,
+                                            plan.freqs_dev, f0, nb, plan.flux, plan.nsrc, w["W2"], None, side)
+                                epi = _lib.make_epilogue(
+                                    obase, sb_, sp_, pmap, pt.kmap.data_ptr() if pt.kmap is not None else 0,
+                                    pt.conj.data_ptr() if pt.conj is not None else 0, accumulate=ch > 0)
+                                nufft2.type1_fused(plan.precision, w["xyz"][0], w["xyz"][1], w["n_dev"], scale,
+                                                   w["W2"][:nb], pt.modes, plan.eps, plan.upsample_factor, epi)
+                            continue
                         if plan.basis is not None:
                             self._basis_batch(plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st,
                                               tiles=tiles)
@@ -564,6 +612,8 @@ class GPUSimulationEngine(SimulationEngine):
                                 # later source chunks add to what is there (cpu_simulate.py:1069 `vis[...] +=`)
                                 accumulate=ch > 0)
                             self._nufft_batch(plan, w, nufft, pt, dim, xlim, scale, nb, epi)
+                    if two:
+                        st.wait_stream(side)                 # chunk complete; the live set may be rewritten
                 if copy_st is not None:
                     self._stream_slab(out, host_out, to, st, copy_st)
                 if slab_hook is not None:
