@@ -360,12 +360,15 @@ def run_gpu(args):
         pl.reset_timing()
     eng.time_stages = True
     eng.stage_times()
+    overlapped = bool(eng.two_streams)
+    eng.two_streams = False                              # kernels one after the other: clean per-stage times
     xe0, xe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     xe0.record()
     step()
     xe1.record()
     barrier()
+    eng.two_streams = overlapped
     extra_ms = xe0.elapsed_time(xe1)
     stages_all = merged_stage_times()
     stages_all.update(eng.stage_times())                 # rotate + cut, beam-tile sort, weights
@@ -443,8 +446,16 @@ def run_gpu(args):
         stage_share = {k: {"ms": v[0], "launches": v[1], "share_of_step": v[0] / extra_ms if extra_ms else None}
                        for k, v in stages_all.items()}
         stage_share["_from"] = {"ms": extra_ms, "launches": 1, "share_of_step": 1.0,
-                                "note": "one extra step after the timed region with every stage timed; the timed "
-                                        "region itself times only the dominant stage (roofline)"}
+                                "note": "one extra step after the timed region with every stage timed and all kernels "
+                                        "on one stream (the timed region overlaps alternate frequency batches on two "
+                                        "streams and times only the dominant stage, for the roofline)"}
+        if roof is not None and plan2.use_type1 and stages_all.get("spread", (0, 0))[1]:
+            sp_ms1, sp_n1 = stages_all["spread"]
+            roof["alone"] = {"avg_launch_ms": sp_ms1 / sp_n1,
+                             "frac": roof["alg_bytes_per_launch"] / (sp_ms1 / sp_n1 * 1e-3) / 1e9 / roof["peak"],
+                             "note": "the same kernel timed in the single-stream extra step (no co-running kernels); "
+                                     "`achieved` / `frac` above are from the timed region, where the launches of two "
+                                     "streams overlap and each launch therefore lasts longer"}
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu_val, cpu_desc, cores, _ = cpu_sample(w, nbls, budget_s=args.cpu_budget)
