@@ -288,7 +288,8 @@ def run_gpu(args):
     beam = w["beam"] if w["polarized"] else w["beam"].to_power()
     beam_list = beam if isinstance(beam, list) else [beam]
     eng = GPUSimulationEngine(freq_batch=args.freq_batch, type1_method=args.type1_method)
-    eng.two_streams = not args.one_stream
+    eng.two_streams = False if args.one_stream else (os.environ.get("FV_TWO_STREAMS") or True)
+    eng.side_streams = int(os.environ.get("FV_SIDE_STREAMS", eng.side_streams))
     if args.no_beam_tiles:
         eng.beam_tiles = False
     elif os.environ.get("FV_BEAM_TILES"):                    # "sort" (default) or "smem"

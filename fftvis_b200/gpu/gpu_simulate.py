@@ -118,10 +118,10 @@ def _copy_stream(dev) -> torch.cuda.Stream:
 _SIDE_STREAMS: dict = {}
 
 
-def _side_stream(dev) -> torch.cuda.Stream:
-    """One side compute stream per device: alternate frequency batches of the fused type-1 path run on it, so
+def _side_stream(dev, i: int = 0) -> torch.cuda.Stream:
+    """Side compute streams of a device: alternate frequency batches of the fused type-1 path run on them, so
     that the tail of one batch's kernels overlaps the head of the next batch's."""
-    key = torch.device(dev).index
+    key = (torch.device(dev).index, i)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
     return _SIDE_STREAMS[key]
@@ -157,6 +157,7 @@ class GPUSimulationEngine(SimulationEngine):
         # (the kernels of consecutive batches then overlap: pass 2's latency-bound waves and the wave tails of
         # pass 1 fill with the other batch's CTAs); False = one stream
         self.two_streams = True
+        self.side_streams = 2                            # measured on cfg2: 178.7 / 174.7 / 172.1 ms per step with 1 / 2 / 3
 
     # ------------------------------------------------------------------------------------------
     def _timed(self, name, st, fn, *a, **k):
@@ -191,8 +192,9 @@ class GPUSimulationEngine(SimulationEngine):
         stream's (for callers that switch the per-stage timers on and read them: bench.py)."""
         plans = [self._nufft_plan(dev)]
         if self.two_streams:
-            with torch.cuda.device(dev), torch.cuda.stream(_side_stream(dev)):
-                plans.append(default_plan())
+            for i in range(max(1, int(self.side_streams))):
+                with torch.cuda.device(dev), torch.cuda.stream(_side_stream(dev, i)):
+                    plans.append(default_plan())
         return plans
 
     def _nufft_plan(self, dev) -> NufftPlan:
@@ -532,14 +534,18 @@ class GPUSimulationEngine(SimulationEngine):
                 copy_st = _copy_stream(dev)
                 copy_st.wait_stream(st)                      # the zero fill precedes every slab copy
             s_f, s_t = out.stride(0), out.stride(1)          # in elements
-            two = bool(self.two_streams and plan.use_type1 and self.type1_method == "fused" and plan.basis is None
-                       and plan.nf_local > plan.freq_batch)
+            two = bool(self.two_streams and plan.basis is None and plan.nf_local > plan.freq_batch and
+                       ((plan.use_type1 and self.type1_method == "fused") or
+                        (not plan.use_type1 and self.two_streams == "all")))
             if two:
-                side = _side_stream(dev)
-                with torch.cuda.stream(side):
-                    nufft2 = default_plan()                   # the side stream's own plan (work buffers, T)
-                if "W2" not in w:
-                    w["W2"] = torch.empty_like(w["W"])
+                nside = max(1, int(self.side_streams))
+                sides = [_side_stream(dev, i) for i in range(nside)]
+                nufft2s = []
+                for sd in sides:
+                    with torch.cuda.stream(sd):
+                        nufft2s.append(default_plan())       # the side stream's own plan (work buffers, T)
+                if len(w.get("W2", [])) < nside:
+                    w["W2"] = [torch.empty_like(w["W"]) for _ in range(nside)]
                 ev_rc = torch.cuda.Event()
             for to, ti in enumerate(range(t_lo, t_hi)):
                 for ch in range(plan.nchunks):
@@ -574,22 +580,24 @@ class GPUSimulationEngine(SimulationEngine):
                             continue                         # nothing above the horizon
                     if two:
                         ev_rc.record(st)
-                        side.wait_event(ev_rc)               # the live set of this (time, chunk) is ready
+                        for sd in sides:
+                            sd.wait_event(ev_rc)             # the live set of this (time, chunk) is ready
                     for jb, f0 in enumerate(range(plan.f_lo, plan.f_hi, plan.freq_batch)):
                         nb = min(plan.freq_batch, plan.f_hi - f0)
                         scale = freqs64[f0:f0 + nb]
                         obase = out.data_ptr() + ((f0 - plan.f_lo) * s_f + to * s_t) * esz
                         sb_, sp_ = s_f, plan.nbls
-                        if two and (jb & 1) and tiles is None:
+                        if two and (jb % (nside + 1)) and tiles is None:
+                            si = jb % (nside + 1) - 1
+                            side, nufft2, W2 = sides[si], nufft2s[si], w["W2"][si]
                             for pt in plan.pairs:
                                 self._timed("weights", side, launch_weights, prec, mode, plan.beams[pt.bi],
                                             plan.beams[pt.bj], w["az"], w["za"], w["src_idx"], w["n_dev"], plan.n_cap,
-                                            plan.freqs_dev, f0, nb, plan.flux, plan.nsrc, w["W2"], None, side)
+                                            plan.freqs_dev, f0, nb, plan.flux, plan.nsrc, W2, None, side)
                                 epi = _lib.make_epilogue(
                                     obase, sb_, sp_, pmap, pt.kmap.data_ptr() if pt.kmap is not None else 0,
                                     pt.conj.data_ptr() if pt.conj is not None else 0, accumulate=ch > 0)
-                                nufft2.type1_fused(plan.precision, w["xyz"][0], w["xyz"][1], w["n_dev"], scale,
-                                                   w["W2"][:nb], pt.modes, plan.eps, plan.upsample_factor, epi)
+                                self._nufft_batch(plan, w, nufft2, pt, dim, xlim, scale, nb, epi, W=W2[:nb])
                             continue
                         if plan.basis is not None:
                             self._basis_batch(plan, w, nufft, mode, dim, xlim, f0, nb, scale, obase, sb_, sp_, st,
@@ -613,7 +621,8 @@ class GPUSimulationEngine(SimulationEngine):
                                 accumulate=ch > 0)
                             self._nufft_batch(plan, w, nufft, pt, dim, xlim, scale, nb, epi)
                     if two:
-                        st.wait_stream(side)                 # chunk complete; the live set may be rewritten
+                        for sd in sides:
+                            st.wait_stream(sd)               # chunk complete; the live set may be rewritten
                 if copy_st is not None:
                     self._stream_slab(out, host_out, to, st, copy_st)
                 if slab_hook is not None:
