@@ -57,7 +57,14 @@ __device__ inline void eval_beam(const fv_beam& b, double az, double za, double 
       e = exp(-(za * za) / (2.0 * s * s));
     } else if (b.kind == 1) {
       const double x = M_PI * b.diameter * sin(za) * freq / kC;
-      e = (x == 0.0) ? 1.0 : 2.0 * j1(x) / x;
+      if (sizeof(T) == 4) {
+        // single precision: the argument in fp64 (it reaches ~30 rad), the Bessel function itself in fp32 -- its
+        // ~1e-7 absolute error is below the rounding of the fp32 strengths it is folded into
+        const float xf = (float)x;
+        e = (x == 0.0) ? 1.0 : (double)(2.0f * j1f(xf) / xf);
+      } else {
+        e = (x == 0.0) ? 1.0 : 2.0 * j1(x) / x;
+      }
     } else {
       e = 1.0;
     }
