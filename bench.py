@@ -401,7 +401,12 @@ def run_gpu(args):
     torch.cuda.empty_cache()
     if strong:
         eng_e = GPUSimulationEngine(freq_batch=args.freq_batch, type1_method=args.type1_method)
-        e2e_call = lambda: fvdist.simulate_vis_sharded(eng_e, dst=0, shards=shards, beam_list=beam_list, **call)
+        # every rank streams its block into a shared page-locked host array (all PCIe links); the variant that
+        # gathers on rank 0's GPU by NCCL and copies from there is timed once as ``e2e.gathered_value``
+        e2e_call = lambda: fvdist.simulate_vis_sharded(eng_e, dst=0, shards=shards, beam_list=beam_list,
+                                                       host_result="shared", **call)
+        e2e_gather_call = lambda: fvdist.simulate_vis_sharded(eng_e, dst=0, shards=shards, beam_list=beam_list,
+                                                              host_result="gather", **call)
     else:
         e2e_call = lambda: fftvis_b200.simulate_vis(beam=w["beam"], **call)
     e2e_val, h2d, d2h, first_s = None, 0, 0, None
@@ -425,6 +430,18 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
         e2e_val = terms(w, nbls) * work_units * e2e_steps / float(tdt.item())
+        e2e_gathered = None
+        if strong:
+            del res
+            wg = e2e_gather_call()                             # warm (page-locks rank 0's result block)
+            del wg
+            barrier()
+            t0 = time.perf_counter()
+            res = e2e_gather_call()
+            barrier()
+            tg = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            e2e_gathered = terms(w, nbls) / float(tg.item())
         csz = 8 * w["precision"]
         h2d = int(np.asarray(w["fluxes"]).size * csz + 3 * 8 * w["nsrc"] + 8 * np.size(w["freqs"]))
         d2h = int(res.size * res.itemsize) if res is not None else 0
@@ -480,8 +497,12 @@ def run_gpu(args):
             "e2e": None if e2e_val is None else
                    {"value": e2e_val, "unit": "terms/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "first_call_s": first_s,
-                    "api": ("fftvis_b200.gpu.distributed.simulate_vis_sharded(host numpy in, host numpy out on rank 0)"
-                            if strong else "fftvis_b200.simulate_vis(host numpy in, host numpy out)")},
+                    "api": ("fftvis_b200.gpu.distributed.simulate_vis_sharded(host numpy in, host numpy out on rank 0; "
+                            "host_result='shared': every rank copies its frequency block into one shared page-locked array)"
+                            if strong else "fftvis_b200.simulate_vis(host numpy in, host numpy out)"),
+                    **({"gathered_value": e2e_gathered,
+                        "gathered_note": "same call with host_result='gather': slabs collected on rank 0's GPU by NCCL, "
+                                         "one D2H link (1 call)"} if strong and e2e_gathered is not None else {})},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

@@ -157,6 +157,39 @@ def shard_inputs(kw: dict, lo: int, hi: int) -> dict:
 _CPU_ONLY = ("nprocesses", "nthreads", "force_use_ray", "trace_mem", "enable_memory_monitor")
 
 
+def _simulate_shared(engine, plan, shards, nfreqs: int, group, root: int):
+    """``host_result="shared"``: this rank's block of the result streamed into the shared host array."""
+    from .gpu_simulate import _CDT, _NP_C
+    rank = dist.get_rank(group)
+    P = 4 if plan.polarized else 1
+    lo, hi = shards[rank]
+    shape = (nfreqs, plan.ntimes, P, plan.nbls)
+    cdt = _NP_C[plan.precision]
+    nbytes = int(np.prod(shape)) * np.dtype(cdt).itemsize
+    st = engine.__dict__.setdefault("_shared_state", {"slot": 0})
+    st["slot"] ^= 1
+    seg = SharedHostResult.get(nbytes, group, root, st["slot"])
+    full = seg.array(shape, cdt)
+    mine = torch.from_numpy(full[lo:hi])                       # contiguous: the frequency axis is the outermost
+    if hi > lo:
+        if seg.registered:
+            engine.run_plan(plan, host_out=mine)
+        else:                                                  # page-locking refused: one plain copy at the end
+            out = engine.run_plan(plan)
+            torch.cuda.current_stream(plan.device).synchronize()
+            mine.copy_(out.cpu())
+    bad = torch.zeros(1, dtype=torch.int32, device=plan.device)
+    if plan.work:
+        bad += (plan.work["counts"] < 0).any().to(torch.int32)
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)    # also orders every rank's copies before the read
+    torch.cuda.current_stream(plan.device).synchronize()
+    if int(bad.item()):
+        engine.check_source_buffer(plan)
+        raise ValueError("source_buffer too small on another rank's frequency shard. Increase source_buffer.")
+    dist.barrier(group)
+    return engine._shape_result(plan, full) if rank == root else None
+
+
 def run_sharded(engine, plan, shards, group=None, dst: int = 0, full: torch.Tensor | None = None,
                 host_out: torch.Tensor | None = None, work: dict | None = None):
     """One frequency-sharded pass with the per-slab gather (see the module docstring).  ``plan`` is this
@@ -209,7 +242,56 @@ def run_sharded(engine, plan, shards, group=None, dst: int = 0, full: torch.Tens
     return full if rank == dst else None
 
 
-def simulate_vis_sharded(engine, *, group=None, dst: int | None = 0, shards=None, **simulate_kwargs):
+class SharedHostResult:
+    """The result array in POSIX shared memory, mapped and page-locked (``cudaHostRegister``) by every rank of
+    one node: each rank streams the finished time slabs of ITS frequency block over its own PCIe link straight
+    into its rows of the ``(nf, nt, P, nbls)`` array, instead of sending them to one rank that owns the only
+    host copy (whose single link then bounds the call).  Two segments alternate between calls, so the array a
+    call returned stays intact during the next call; segments are cached per size."""
+
+    _cache: dict = {}
+
+    def __init__(self, nbytes: int, group, root: int, tag: int):
+        from multiprocessing import shared_memory
+        rank = dist.get_rank(group)
+        name = [None]
+        if rank == root:
+            self.shm = shared_memory.SharedMemory(create=True, size=max(int(nbytes), 1))
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=dist.get_global_rank(group, root) if group is not None else root,
+                                   group=group)
+        if rank != root:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        if rank != root:
+            try:                              # attaching registered the segment with this process' resource tracker,
+                from multiprocessing import resource_tracker      # which would unlink it again at exit
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.owner = rank == root
+        self.nbytes = int(nbytes)
+        self.bytes_view = np.ndarray((self.nbytes,), dtype=np.uint8, buffer=self.shm.buf)
+        self.registered = False
+        if torch.cuda.is_available() and self.nbytes:
+            rc = torch.cuda.cudart().cudaHostRegister(self.bytes_view.ctypes.data, self.nbytes, 0)
+            self.registered = int(rc) == 0
+        dist.barrier(group)
+        if rank == root:
+            self.shm.unlink()                 # the mappings keep it alive; nothing is left behind in /dev/shm
+
+    @classmethod
+    def get(cls, nbytes: int, group, root: int, slot: int):
+        key = (int(nbytes), id(group), int(root), int(slot))
+        if key not in cls._cache:
+            cls._cache[key] = cls(nbytes, group, root, slot)
+        return cls._cache[key]
+
+    def array(self, shape, dtype) -> np.ndarray:
+        return np.ndarray(tuple(shape), dtype=dtype, buffer=self.shm.buf)
+
+
+def simulate_vis_sharded(engine, *, group=None, dst: int | None = 0, shards=None, host_result: str = "gather",
+                         **simulate_kwargs):
     """Frequency-sharded ``simulate``: every rank passes the SAME full inputs (the arguments of
     ``GPUSimulationEngine.simulate``); rank ``dst`` (or every rank when ``dst`` is None) returns the full
     host array ``(nf, nt, [2, 2,] nbls)``, the others ``None``.
@@ -218,7 +300,14 @@ def simulate_vis_sharded(engine, *, group=None, dst: int | None = 0, shards=None
     ``fluxes``, ``beam_coefs``, tabulated beams) are ALREADY this rank's block -- for workloads whose
     full per-frequency inputs should never exist on one host (cfg5: 21 GB of basis-beam tables).
 
+    ``host_result``: ``"gather"`` -- the finished time slabs are collected on ``dst``'s GPU by NCCL and copied to
+    its page-locked result from there (the gathered array also stays device-resident on ``dst``);
+    ``"shared"`` (ranks of one node, ``dst`` not None) -- every rank streams its own block straight into a
+    shared page-locked host array (``SharedHostResult``): no device-side gather, all PCIe links in use.
+
     ``engine`` is a ``GPUSimulationEngine`` bound to this rank's device."""
+    if host_result not in ("gather", "shared"):
+        raise ValueError("host_result must be 'gather' or 'shared'")
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     kw = {k: v for k, v in simulate_kwargs.items() if k not in _CPU_ONLY}
@@ -234,6 +323,8 @@ def simulate_vis_sharded(engine, *, group=None, dst: int | None = 0, shards=None
             raise ValueError("with shards=..., freqs must be this rank's block of the frequency axis")
     plan = engine.prepare(**kw)
     P = 4 if plan.polarized else 1
+    if host_result == "shared" and dst is not None:
+        return _simulate_shared(engine, plan, shards, nfreqs, group, root)
     host = None
     if rank == root:
         from .gpu_simulate import _CDT

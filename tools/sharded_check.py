@@ -19,7 +19,12 @@ kw = dict(ants=ants, freqs=freqs, fluxes=flux, beam_list=[AiryBeam(diameter=14.0
           telescope_loc=HERA_LOCATION, precision=2, eps=1e-12)
 eng = GPUSimulationEngine()
 got = simulate_vis_sharded(eng, dst=0, **kw)
+shared = simulate_vis_sharded(eng, dst=0, host_result="shared", **kw)
+shared2 = simulate_vis_sharded(eng, dst=0, host_result="shared", **kw)       # the other segment
 if rank == 0:
+    print("shared host block equals the gathered result:", bool(np.array_equal(shared, got)),
+          bool(np.array_equal(shared2, got)), flush=True)
+    assert np.array_equal(shared, got) and np.array_equal(shared2, got)
     ref = eng.simulate(**kw)
     err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
     print(f"sharded over {dist.get_world_size()} ranks vs single GPU: rel err {err:.2e}", flush=True)
