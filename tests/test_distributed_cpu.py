@@ -111,3 +111,40 @@ def test_shard_inputs_cuts_the_frequency_axis():
     assert s["freqs"].tolist() == [3.0, 4.0, 5.0] and s["fluxes"].shape == (3, 3) and s["beam_coefs"].shape == (4, 2, 3)
     assert s["eps"] == 1e-9 and kw["fluxes"].shape == (3, 10)
     assert shard_inputs(dict(freqs=np.arange(4.0), fluxes=np.ones((2, 4, 2, 2))), 0, 2)["fluxes"].shape == (2, 2, 2, 2)
+
+
+def _shared_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fftvis_b200.gpu.distributed import SharedHostResult
+        shards = shard_frequencies(5, world)
+        shape, ok = (5, 2, 1, 3), True
+        for slot in (0, 1, 0):                                 # two alternating segments, then the cached first one
+            seg = SharedHostResult.get(int(np.prod(shape)) * 16, None, 0, slot)
+            full = seg.array(shape, np.complex128)
+            lo, hi = shards[rank]
+            full[lo:hi] = (rank + 1) * (slot + 1) + 1j * np.arange(lo, hi)[:, None, None, None]
+            dist.barrier()
+            if rank == 0:
+                for r, (a, b) in enumerate(shards):
+                    ok &= bool(np.all(full[a:b].real == (r + 1) * (slot + 1)))
+                    ok &= bool(np.all(full[a:b].imag == np.arange(a, b)[:, None, None, None]))
+            dist.barrier()
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_host_result_gloo_world2():
+    """Every rank writes its frequency block into the shared host array; rank 0 reads all of them."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shared_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
