@@ -121,7 +121,7 @@ extern "C" int fv_plan_destroy(fv_plan* P) {
   if (P->small) cudaFree(P->small);
   if (P->rec) cudaFree(P->rec);
   for (auto& kv : P->small_scheds) { cudaFree(kv.second.ph_off); cudaFree(kv.second.ph_bins); }
-  for (auto& kv : P->smem_ffts) { cudaFree(kv.second.tw); if (kv.second.pos_dev) cudaFree(kv.second.pos_dev); }
+  for (auto& kv : P->smem_ffts) { cudaFree(kv.second.tw); if (kv.second.pos_dev) cudaFree(kv.second.pos_dev); if (kv.second.wn) cudaFree(kv.second.wn); }
   delete P;
   return FV_OK;
 }
@@ -228,6 +228,9 @@ extern "C" int fv_plan_set_option(fv_plan* P, const char* name, int64_t value) {
   else if (n == "t1_small") P->t1_small = (int)value;
   else if (n == "t1_xdirect") P->t1_xdirect = (int)value;
   else if (n == "timing_mask") P->timing_mask = (int)value;
+  else if (n == "t3_half") P->t3_half = (int)value;
+  else if (n == "t3_minby") P->t3_minb[1] = (int)value;
+  else if (n == "t3_minbz") P->t3_minb[2] = (int)value;
   else if (n == "t3_fft") P->t3_fft = (int)value;
   else if (n.rfind("t3_v", 0) == 0 && n.size() == 5 && n[4] >= 'x' && n[4] <= 'z') P->t3_v[n[4] - 'x'] = (int)value;
   else if (n.rfind("t3_thr", 0) == 0 && n.size() == 7 && n[6] >= 'x' && n[6] <= 'z') P->t3_thr[n[6] - 'x'] = (int)value;

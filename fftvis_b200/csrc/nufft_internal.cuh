@@ -502,7 +502,8 @@ struct fv_plan {
   std::vector<cudaEvent_t> event_pool;
   size_t max_grid_bytes = (size_t)96 << 30;   // refuse grids beyond this (B200 has 180 GB)
   // shared-memory FFT plans of the fused type-1 path, keyed by (prec, nf)
-  struct SmemFft { fv::FftStages st; void* tw = nullptr; std::vector<int> pos; int32_t* pos_dev = nullptr; };
+  struct SmemFft { fv::FftStages st; void* tw = nullptr; std::vector<int> pos; int32_t* pos_dev = nullptr;
+                   void* wn = nullptr; };   // wn: exp(+2 pi i j / (2 n)), j < n (half-length type-3 passes)
   std::map<std::pair<int, int64_t>, SmemFft> smem_ffts;
   void* tbuf = nullptr; size_t tbuf_bytes = 0;   // half-transformed array T of the fused type-1 path
   void* prep = nullptr; size_t prep_bytes = 0;   // folded NU points (ix0, iy0, zx, zy) of the current batch
@@ -513,6 +514,8 @@ struct fv_plan {
   int t3_fft = 1;                                // 0: cuFFT on the padded grid; 1: own pruned shared-memory passes for 3-D
                                                  // (where they measure faster), cuFFT for 2-D; 2: own passes always
   int t3_v[3] = {0, 0, 0}, t3_thr[3] = {0, 0, 0}; // tuning overrides: vectors per CTA / threads of the x, y, z passes
+  int t3_half = 6;                               // bit d: half-length pass along dimension d where ng = 2 nf (0: full-length forms); measured on cfg4: y + z
+  int t3_minb[3] = {0, 0, 0};                    // CTAs per SM the half-length y / z passes are compiled for (0: automatic)
   int t1_rows = 0;                               // strip height override (0 = automatic)
   int t1_cols = 0;                               // columns per CTA override (0 = automatic)
   // small-grid type-1 path (type1_small.cuh): sort buffers, records, per-(nf, w) phase schedules

@@ -42,6 +42,37 @@ static int device_limits(fv_plan* P, const T* const* arr, int dim, const int32_t
   return FV_OK;
 }
 
+// half-length strided pass (y: d = 1, z: d = 2): vectors per CTA and CTAs per SM from the shared memory one CTA needs
+template <typename T>
+static int launch_half_strided(fv_plan* P, T3FftArgs<T> fa, fv_plan::SmemFft* Fh, int64_t nh, int d, int64_t ninner,
+                               int64_t nouter, int q, int vfit) {
+  using C = cplx_t<T>;
+  int v = vfit;
+  if (P->t3_v[d] > 0) v = std::min(v, P->t3_v[d]);
+  if (v >= 4) v -= v % 2;
+  int minb = P->t3_minb[d];
+  if (minb == 0) minb = d == 2 ? 4 : 1;      // z: short vectors, occupancy-bound (cfg4: 26 -> 14 ms per 4 transforms); y: no gain measured
+  // several CTAs per SM: each gets its share of shared memory
+  if (minb > 1) {
+    const size_t budget = (size_t)(220 * 1024) / minb;
+    while (v > 1 && sizeof(C) * ((size_t)v * (nh + 1) + nh) > budget) --v;
+  }
+  fa.nvec_cta = v; fa.tw = (const C*)Fh->tw; fa.st = Fh->st; fa.pos = Fh->pos_dev;
+  const size_t smem = sizeof(C) * ((size_t)v * (nh + 1) + nh);
+  dim3 g((unsigned)(nouter * ceil_div(ninner, v)), q);
+  const C* wn = (const C*)Fh->wn;
+#define FV_T3H(MB, THR)                                                                                        \
+  {                                                                                                            \
+    auto kern = t3_fft_half_strided_kernel<T, MB>;                                                             \
+    FV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+    kern<<<g, THR, smem, P->stream>>>(fa, wn);                                                                 \
+  }
+  if (minb >= 4) FV_T3H(4, 256) else if (minb >= 2) FV_T3H(2, 256) else FV_T3H(1, (P->t3_thr[d] > 0 ? P->t3_thr[d] : 512))
+#undef FV_T3H
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
 template <typename T>
 static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void* y, const void* z,
                        const int32_t* n_dev, int64_t n_cap, const double* xlim_in, const void* u,
@@ -187,6 +218,37 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
       }
     }
   }
+  // half-length passes (type3_fft.cuh): ng = 2 nf with nf even, and a shared-memory plan for nf
+  fv_plan::SmemFft* Fh[3] = {nullptr, nullptr, nullptr};
+  bool halfd[3] = {false, false, false};
+  if (own_fft && P->t3_half) {
+    for (int d = 0; d < dim; ++d) {
+      if (!((P->t3_half >> d) & 1) || ng[d] != 2 * nf[d] || (nf[d] & 1)) continue;
+      if (get_smem_fft(P, prec, nf[d], &Fh[d]) != FV_OK) { Fh[d] = nullptr; continue; }
+      if (!Fh[d]->pos_dev) {
+        FV_CUDA(cudaMalloc((void**)&Fh[d]->pos_dev, sizeof(int) * nf[d]));
+        FV_CUDA(cudaMemcpyAsync(Fh[d]->pos_dev, Fh[d]->pos.data(), sizeof(int) * nf[d], cudaMemcpyHostToDevice, P->stream));
+        FV_CUDA(cudaStreamSynchronize(P->stream));
+      }
+      if (!Fh[d]->wn) {
+        std::vector<C> h(nf[d]);
+        for (int64_t j = 0; j < nf[d]; ++j) {
+          const double ang = M_PI * (double)j / (double)nf[d];                 // 2 pi j / (2 nf)
+          h[j] = make_c<T>((T)cos(ang), (T)sin(ang));
+        }
+        FV_CUDA(cudaMalloc(&Fh[d]->wn, sizeof(C) * nf[d]));
+        FV_CUDA(cudaMemcpyAsync(Fh[d]->wn, h.data(), sizeof(C) * nf[d], cudaMemcpyHostToDevice, P->stream));
+        FV_CUDA(cudaStreamSynchronize(P->stream));
+      }
+      halfd[d] = true;
+    }
+  }
+  auto vec_fit_half = [&](int64_t nh, int cap) {
+    const int64_t room = (int64_t)smem_fft_max / (int64_t)sizeof(C) - nh;
+    int v = (int)std::max<int64_t>(0, std::min<int64_t>(cap, room / (nh + 1)));
+    while (v > 1 && (int64_t)v * nh >= 65536) --v;                            // exact 32-bit index division in the kernels
+    return v;
+  };
   const size_t cells3 = dim == 3 ? (size_t)nf[2] * ng[1] * ng[0] : (size_t)nf[1] * ng[0];
   {
     int64_t* g = P->last_geo;
@@ -239,11 +301,22 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
         fa.nvec = nf[1] * nf[2]; fa.in_q = (int64_t)cells1; fa.out_q = dim == 3 ? (int64_t)cells2 : nf[1] * ng[0];
         fa.inv1 = inv1; fa.inv2 = inv2; fa.inv3 = inv3; fa.nf2 = (int)nf[1];
         fa.tw = (const C*)F[0]->tw; fa.st = F[0]->st; fa.pos = F[0]->pos_dev;
+        if (halfd[0]) {
+          int v = vec_fit_half(nf[0], 16);
+          if (P->t3_v[0] > 0) v = std::min(v, P->t3_v[0]);
+          fa.nvec_cta = v; fa.tw = (const C*)Fh[0]->tw; fa.st = Fh[0]->st; fa.pos = Fh[0]->pos_dev;
+          const size_t smem = sizeof(C) * ((size_t)v * (nf[0] + 1) + nf[0]);
+          FV_CUDA(cudaFuncSetAttribute(t3_fft_half_contig_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          dim3 g(ceil_div(fa.nvec, v), q);
+          t3_fft_half_contig_kernel<T><<<g, thx, smem, P->stream>>>(fa, (const C*)Fh[0]->wn);
+          FV_LAUNCH_CHECK();
+        } else {
         const size_t smem = sizeof(C) * ((size_t)vx * (ng[0] + 1) + ng[0]);
         FV_CUDA(cudaFuncSetAttribute(t3_fft_contig_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 g(ceil_div(fa.nvec, vx), q);
         t3_fft_contig_kernel<T><<<g, thx, smem, P->stream>>>(fa);
         FV_LAUNCH_CHECK();
+        }
       }
       {
         T3FftArgs<T> fa{};
@@ -252,11 +325,16 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
         fa.in_q = dim == 3 ? (int64_t)cells2 : nf[1] * ng[0]; fa.in_a = nf[1] * ng[0]; fa.in_k = ng[0];
         fa.out_q = dim == 3 ? nf[2] * ng[1] * ng[0] : (int64_t)cells2; fa.out_a = ng[1] * ng[0]; fa.out_k = ng[0];
         fa.tw = (const C*)F[1]->tw; fa.st = F[1]->st; fa.pos = F[1]->pos_dev;
+        if (halfd[1]) {
+          rc = launch_half_strided<T>(P, fa, Fh[1], nf[1], 1, (int64_t)ng[0], (int64_t)nf[2], q, vec_fit_half(nf[1], 16));
+          if (rc) return rc;
+        } else {
         const size_t smem = sizeof(C) * ((size_t)vy * (ng[1] + 1) + ng[1]);
         FV_CUDA(cudaFuncSetAttribute(t3_fft_strided_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 g((unsigned)(nf[2] * ceil_div(ng[0], vy)), q);
         t3_fft_strided_kernel<T><<<g, thy, smem, P->stream>>>(fa);
         FV_LAUNCH_CHECK();
+        }
       }
       if (dim == 3) {
         T3FftArgs<T> fa{};
@@ -265,11 +343,16 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
         fa.in_q = nf[2] * ng[1] * ng[0]; fa.in_a = 0; fa.in_k = ng[1] * ng[0];
         fa.out_q = (int64_t)cells2; fa.out_a = 0; fa.out_k = ng[1] * ng[0];
         fa.tw = (const C*)F[2]->tw; fa.st = F[2]->st; fa.pos = F[2]->pos_dev;
+        if (halfd[2]) {
+          rc = launch_half_strided<T>(P, fa, Fh[2], nf[2], 2, (int64_t)(ng[1] * ng[0]), 1, q, vec_fit_half(nf[2], 64));
+          if (rc) return rc;
+        } else {
         const size_t smem = sizeof(C) * ((size_t)vz * (ng[2] + 1) + ng[2]);
         FV_CUDA(cudaFuncSetAttribute(t3_fft_strided_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 g((unsigned)ceil_div(ng[1] * ng[0], vz), q);
         t3_fft_strided_kernel<T><<<g, thz, smem, P->stream>>>(fa);
         FV_LAUNCH_CHECK();
+        }
       }
     } else {
       {

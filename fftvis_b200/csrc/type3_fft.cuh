@@ -154,4 +154,90 @@ t3_fft_strided_kernel(T3FftArgs<T> a) {
   }
 }
 
+// ---- half-length form (ng = 2 nf exactly, nf even: upsampling factor 2, every BASELINE config) -------------------
+// The padded vector holds its nin = n / 2 centred modes at the two ends of the n-point grid.  Shifted by nin / 2 it
+// is y[j] = data[j], j < nin, followed by nin zeros, and the shift costs a factor (-i)^k on the outputs.  The first
+// decimation-in-frequency stage of a vector whose second half is zero is free:
+//     X[2k']     = (-1)^k'        FFT_nin( y[j] )[k']
+//     X[2k' + 1] = (-1)^k' (-i)   FFT_nin( y[j] exp(+2 pi i j / n) )[k']
+// so the pass runs two nin-point transforms per vector on half-length shared-memory vectors (twice the vectors per
+// CTA, or twice the CTAs per SM, for the same shared memory), reading the input twice (the second time from L2).
+template <typename T>
+__device__ __forceinline__ cplx_t<T> t3_half_out(cplx_t<T> v, int k, int half) {
+  // (-1)^k, and for the odd outputs a further factor -i
+  if (k & 1) { v.x = -v.x; v.y = -v.y; }
+  if (half) { const T t = v.x; v.x = v.y; v.y = -t; }
+  return v;
+}
+
+template <typename T, int MINB>
+__global__ void __launch_bounds__(MINB > 1 ? 256 : 512, MINB)
+t3_fft_half_strided_kernel(T3FftArgs<T> a, const cplx_t<T>* __restrict__ wn) {
+  using C = cplx_t<T>;
+  extern __shared__ __align__(16) unsigned char t3f_smem[];
+  C* vecs = (C*)t3f_smem;                         // nvec_cta * pitch, vector = one inner column, nin points
+  const int nin = a.nin, pitch = nin + 1, cb = a.nvec_cta;
+  C* tw = vecs + (size_t)cb * pitch;
+  const int tiles = (a.ninner + cb - 1) / cb;
+  const int outer = blockIdx.x / tiles, tile = blockIdx.x - outer * tiles;
+  const int c0 = tile * cb, nc = min(cb, a.ninner - c0);
+  const int q = blockIdx.y;
+  const C* in = a.in + (int64_t)q * a.in_q + (int64_t)outer * a.in_a + c0;
+  C* out = a.out + (int64_t)q * a.out_q + (int64_t)outer * a.out_a + c0;
+  const unsigned inv_nc = nc > 1 ? 0xFFFFFFFFu / (unsigned)nc + 1u : 0u;     // exact i / nc for i < 2^16 * nc ... (i < 2^31 / nc)
+  for (int i = threadIdx.x; i < a.st.tw_len; i += blockDim.x) tw[i] = a.tw[i];
+  for (int half = 0; half < 2; ++half) {
+    for (int i = threadIdx.x; i < nin * nc; i += blockDim.x) {
+      const int k = inv_nc ? (int)__umulhi((unsigned)i, inv_nc) : i, c = i - k * nc;
+      C x = in[(int64_t)k * a.in_k + c];
+      if (half) x = cmul(x, wn[k]);
+      vecs[c * pitch + k] = x;
+    }
+    __syncthreads();
+    smem_fft_cta<T>(vecs, nc, pitch, nin, tw, a.st);
+    for (int i = threadIdx.x; i < nin * nc; i += blockDim.x) {
+      const int k = inv_nc ? (int)__umulhi((unsigned)i, inv_nc) : i, c = i - k * nc;
+      out[(int64_t)(2 * k + half) * a.out_k + c] = t3_half_out<T>(vecs[c * pitch + a.pos[k]], k, half);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512)
+t3_fft_half_contig_kernel(T3FftArgs<T> a, const cplx_t<T>* __restrict__ wn) {
+  using C = cplx_t<T>;
+  extern __shared__ __align__(16) unsigned char t3f_smem[];
+  C* vecs = (C*)t3f_smem;                         // nvec_cta * pitch
+  const int nin = a.nin, n = 2 * nin, pitch = nin + 1;
+  C* tw = vecs + (size_t)a.nvec_cta * pitch;
+  const int64_t v0 = (int64_t)blockIdx.x * a.nvec_cta;
+  const int nv = (int)min((int64_t)a.nvec_cta, a.nvec - v0);
+  const int q = blockIdx.y;
+  const C* in = a.in + (int64_t)q * a.in_q + v0 * nin;
+  C* out = a.out + (int64_t)q * a.out_q + v0 * n;
+  const unsigned inv_nin = 0xFFFFFFFFu / (unsigned)nin + 1u;
+  for (int i = threadIdx.x; i < a.st.tw_len; i += blockDim.x) tw[i] = a.tw[i];
+  for (int half = 0; half < 2; ++half) {
+    for (int i = threadIdx.x; i < nv * nin; i += blockDim.x) {
+      const int v = (int)__umulhi((unsigned)i, inv_nin), k = i - v * nin;
+      const int64_t vg = v0 + v;
+      const int s3 = (int)(vg / a.nf2), s2 = (int)(vg - (int64_t)s3 * a.nf2);
+      T sc = a.inv1[k] * a.inv2[s2];
+      if (a.inv3) sc *= a.inv3[s3];
+      C x = in[i];
+      x.x *= sc; x.y *= sc;
+      if (half) x = cmul(x, wn[k]);
+      vecs[v * pitch + k] = x;
+    }
+    __syncthreads();
+    smem_fft_cta<T>(vecs, nv, pitch, nin, tw, a.st);
+    for (int i = threadIdx.x; i < nv * nin; i += blockDim.x) {
+      const int v = (int)__umulhi((unsigned)i, inv_nin), k = i - v * nin;
+      out[(int64_t)v * n + 2 * k + half] = t3_half_out<T>(vecs[v * pitch + a.pos[k]], k, half);
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace fv

@@ -112,7 +112,10 @@ t3_col_spread_kernel(T3SpreadArgs<T> a) {
   const int tile = blockIdx.x, ty = tile / a.g.ntx, tx = tile - ty * a.g.ntx;
   const int bpi = blockIdx.y, b = bpi / a.ntr;
   const int nf0 = a.g.nf[0], nf1 = a.g.nf[1], nf2 = a.g.nf[2];
-  const int gx = tx * T3_TILE + (tid & (T3_TILE - 1)), gy = ty * T3_TILE + tid / T3_TILE;
+  // a warp owns a 4 x 8 patch of columns (not two 16-column rows): a w x w footprint then covers whole warps or
+  // none of them more often, so fewer warps run the z loop with most of their lanes switched off
+  const int wrp = tid >> 5, ln = tid & 31;
+  const int gx = tx * T3_TILE + 8 * (wrp & 1) + (ln & 7), gy = ty * T3_TILE + 4 * (wrp >> 1) + (ln >> 3);
   const bool owner = gx < nf0 && gy < nf1;
   C acc[T3_NZMAX];
 #pragma unroll

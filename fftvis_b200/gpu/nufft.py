@@ -60,7 +60,8 @@ class NufftPlan:
         self._h = h
         for env, opt in (("FV_T1_ROWS", "t1_rows"), ("FV_T1_COLS", "t1_cols"), ("FV_T3_VX", "t3_vx"),
                          ("FV_T3_VY", "t3_vy"), ("FV_T3_VZ", "t3_vz"), ("FV_T3_THRX", "t3_thrx"),
-                         ("FV_T3_THRY", "t3_thry"), ("FV_T3_THRZ", "t3_thrz")):   # tuning experiments
+                         ("FV_T3_THRY", "t3_thry"), ("FV_T3_THRZ", "t3_thrz"), ("FV_T3_HALF", "t3_half"),
+                         ("FV_T3_MINBY", "t3_minby"), ("FV_T3_MINBZ", "t3_minbz")):   # tuning experiments
             if os.environ.get(env):
                 self.set_option(opt, int(os.environ[env]))
 

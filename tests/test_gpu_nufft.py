@@ -265,19 +265,27 @@ def test_type3_pruned_fft_matches_cufft_path(prec, dim):
     n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
     plan = default_plan()
     outs = []
-    for own in (2, 0):
+    # own passes in the half-length form (where ng = 2 nf: two nf-point transforms per padded vector), own passes
+    # at full length, cuFFT on the padded grid
+    for own, half in ((2, 1), (2, 0), (0, 0)):
         plan.set_option("t3_fft", own)
+        plan.set_option("t3_half", half)
         out = torch.zeros((nb, ntr, nk), dtype=cdt, device="cuda")
         epi = _lib.make_epilogue(out.data_ptr(), out.stride(0), out.stride(1))
         plan.type3(prec, dim, xs, n_dev, None, us, None, scale, Wd, eps, 2.0, epi)
         outs.append(out.cpu().numpy())
+    geo = plan.last_type3_geometry()
     plan.set_option("t3_fft", 1)
+    plan.set_option("t3_half", 1)
+    # the half-length form really ran in at least one dimension of this case
+    assert any(g == 2 * f and f % 2 == 0 for f, g in zip(geo["nf"], geo["ng"])), geo
     for b in range(nb):
         uu = [(a * rd(scale[b])).astype(rd) for a in u]
         want = nc.direct_sum(x[0], x[1], x[2] if dim == 3 else None, W[b], uu[0], uu[1], uu[2] if dim == 3 else None)
         tol = 10 * eps if prec == 2 else f32_bar(nc.nufft_type3(x, W[b], uu, eps), want, eps)
-        assert relerr(outs[0][b], want) < tol
-        assert relerr(outs[1][b], want) < tol
+        for o in outs:
+            assert relerr(o[b], want) < tol
+        assert relerr(outs[0][b], outs[2][b]) < (1e-12 if prec == 2 else 2 * tol)
         assert relerr(outs[0][b], outs[1][b]) < (1e-12 if prec == 2 else 2 * tol)
 
 
