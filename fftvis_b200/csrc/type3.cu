@@ -153,6 +153,7 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
   const bool tiled = dim == 3 && P->t3_tiles && nf[2] <= T3_NZMAX && n_cap > 0;
   T3Geom<T> geo{};
   int32_t *bin_counts = nullptr, *bin_offsets = nullptr, *bin_cursor = nullptr, *bin_list = nullptr;
+  T* t3_rows = nullptr; int32_t* t3_cells = nullptr;
   int ntiles = 0;
   if (tiled) {
     geo.x = xs[0]; geo.y = xs[1]; geo.z = xs[2]; geo.n_dev = n_dev; geo.w = w;
@@ -186,6 +187,16 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
     FV_CUDA(cub::DeviceSegmentedSort::SortKeys(P->scan_tmp, tmp, bin_list, sorted, nitems, ntiles, bin_offsets, bin_offsets + 1, P->stream));
     ++fv::g_launches;
     bin_list = sorted;
+    // kernel rows + first cells of every live source (shared by every frequency and product of the batch)
+    const int wmax_rec = (w == 7 || w == 9 || w == 11 || w == 13 || w == 14) ? w : kMaxW;
+    rc = ensure(&P->rec, &P->rec_bytes, (size_t)n_cap * 3 * (wmax_rec * sizeof(T) + sizeof(int32_t)) + 64);
+    if (rc) return rc;
+    t3_rows = (T*)P->rec;
+    t3_cells = (int32_t*)(t3_rows + (size_t)n_cap * 3 * wmax_rec);
+    const unsigned rblocks = (unsigned)ceil_div(3 * n_cap, 256);
+    FV_DISPATCH_W(w, (t3_records_kernel<T, WT><<<rblocks, 256, 0, P->stream>>>(geo, (T)beta, (T)(4.0 / ((double)w * w)),
+                                                                              (T)(w / 2.0), t3_rows, t3_cells)));
+    FV_LAUNCH_CHECK();
   }
 
   // own pruned FFT passes when every padded dimension's vectors fit shared memory
@@ -269,7 +280,7 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
       ta.g = geo; ta.n_cap = n_cap; ta.beta = (T)beta; ta.c = (T)(4.0 / ((double)w * w)); ta.halfw = (T)(w / 2.0);
       ta.ntr = ntr; ta.prephase = prephase ? 1 : 0;
       ta.W = (const C*)W + (int64_t)b0 * ntr * n_cap; ta.bp = P->bp_dev + b0;
-      ta.offsets = bin_offsets; ta.list = bin_list; ta.grid = (C*)P->grid;
+      ta.offsets = bin_offsets; ta.list = bin_list; ta.rows = t3_rows; ta.cells = t3_cells; ta.grid = (C*)P->grid;
       StageScope ts(P, FV_STAGE_SPREAD);
       dim3 tg(ntiles, sub * ntr);
       FV_DISPATCH_W(w, (t3_col_spread_kernel<T, WT><<<tg, T3_TILE * T3_TILE, 0, P->stream>>>(ta)));

@@ -11,6 +11,8 @@
 //                                every tile's list is then sorted by source index (cub segmented sort), so the
 //                                summation order -- and the result, bit for bit -- does not depend on the order in
 //                                which the fill pass's atomic cursors were served
+//   t3_records_kernel            the w kernel samples per dimension and the first cells of every live source, once
+//                                per batch geometry
 //   t3_col_spread_kernel         one CTA per (tile, frequency, product), one thread per column:
 //                                walk the tile's list; a thread whose column is inside the source's
 //                                (x, y) footprint adds W k_x k_y k_z[.] to its register column; at the
@@ -85,6 +87,28 @@ t3_bin_kernel(T3Geom<T> g, int32_t* __restrict__ counts, const int32_t* __restri
     }
 }
 
+// Kernel rows of every live source, evaluated ONCE per batch geometry (a source sits in ~3 tile lists and the
+// lists are walked again for every frequency and product): record s = three rows of WMAX samples (x, y, z) and
+// the three first cells.  One thread per (source, dimension).
+template <typename T, int WT>
+__global__ void __launch_bounds__(256)
+t3_records_kernel(T3Geom<T> g, T beta, T c, T halfw, T* __restrict__ rows, int32_t* __restrict__ cells) {
+  const int w = WT > 0 ? WT : g.w;
+  constexpr int WMAX = WT > 0 ? WT : kMaxW;
+  const int n = *g.n_dev;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t s = t / 3;
+  if (s >= n) return;
+  const int d = (int)(t - 3 * s);
+  const T v = d == 0 ? g.x[s] : (d == 1 ? g.y[s] : g.z[s]);
+  int i0; T z0;
+  t3_fold<T>(g, d, v, &i0, &z0);
+  cells[3 * s + d] = i0;
+  T* r = rows + (3 * s + d) * WMAX;
+#pragma unroll
+  for (int j = 0; j < WMAX; ++j) r[j] = j < w ? es_kernel<T>(z0 + (T)j, beta, c, halfw) : T(0);
+}
+
 template <typename T>
 struct T3SpreadArgs {
   T3Geom<T> g;
@@ -95,6 +119,8 @@ struct T3SpreadArgs {
   const BatchParams* bp;        // D per frequency (pre-phase)
   const int32_t* offsets;       // (ntiles + 1)
   const int32_t* list;
+  const T* rows;                // (n_cap, 3, WMAX) kernel rows from t3_records_kernel
+  const int32_t* cells;         // (n_cap, 3) first cells
   cplx_t<T>* grid;              // (nb, ntr, nf2, nf1, nf0)
 };
 
@@ -104,7 +130,7 @@ t3_col_spread_kernel(T3SpreadArgs<T> a) {
   using C = cplx_t<T>;
   const int w = WT > 0 ? WT : a.g.w;
   constexpr int WMAX = WT > 0 ? WT : kMaxW;
-  __shared__ int s_ix[T3_RS], s_iy[T3_RS], s_iz[T3_RS];
+  __shared__ int s_ix[T3_RS], s_iy[T3_RS], s_iz[T3_RS], s_src[T3_RS];
   __shared__ T s_k[3][T3_RS][WMAX];     // kernel rows of the staged sources (x, y, z)
   __shared__ __align__(16) T s_kzr[T3_RS][T3_NZMAX];   // z row rotated onto the grid: value for cell z, 0 outside
   __shared__ C s_w[T3_RS];
@@ -127,37 +153,21 @@ t3_col_spread_kernel(T3SpreadArgs<T> a) {
     const int rn = min(T3_RS, l1 - r0);
     if (tid < rn) {
       const int s = a.list[r0 + tid];
-      const T xs = a.g.x[s], ys = a.g.y[s], zs = a.g.z[s];
-      // the first kernel argument of each dimension is parked in slot 0 until the rows are built
-      t3_fold<T>(a.g, 0, xs, &s_ix[tid], &s_k[0][tid][0]);
-      t3_fold<T>(a.g, 1, ys, &s_iy[tid], &s_k[1][tid][0]);
-      t3_fold<T>(a.g, 2, zs, &s_iz[tid], &s_k[2][tid][0]);
+      s_src[tid] = s;
+      s_ix[tid] = a.cells[3 * s]; s_iy[tid] = a.cells[3 * s + 1]; s_iz[tid] = a.cells[3 * s + 2];
       C cw = Wp[s];
       if (a.prephase) {
         double sn, cs;
-        sincos(bpar.D[0] * (double)xs + bpar.D[1] * (double)ys + bpar.D[2] * (double)zs, &sn, &cs);
+        sincos(bpar.D[0] * (double)a.g.x[s] + bpar.D[1] * (double)a.g.y[s] + bpar.D[2] * (double)a.g.z[s], &sn, &cs);
         cw = cmul(cw, make_c<T>((T)cs, (T)sn));
       }
       s_w[tid] = cw;
     }
     __syncthreads();
-    // kernel rows: 3 * rn * w evaluations shared by the whole CTA
-    T kv[3][(T3_RS * WMAX + T3_TILE * T3_TILE - 1) / (T3_TILE * T3_TILE)];
-#pragma unroll
-    for (int q = 0; q < (T3_RS * WMAX + T3_TILE * T3_TILE - 1) / (T3_TILE * T3_TILE); ++q) {
-      const int e = tid + q * T3_TILE * T3_TILE, rr = e / WMAX, jj = e - rr * WMAX;
-      const bool mk = rr < rn && jj < w;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) kv[d][q] = mk ? es_kernel<T>(s_k[d][rr][0] + (T)jj, a.beta, a.c, a.halfw) : T(0);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < (T3_RS * WMAX + T3_TILE * T3_TILE - 1) / (T3_TILE * T3_TILE); ++q) {
-      const int e = tid + q * T3_TILE * T3_TILE, rr = e / WMAX, jj = e - rr * WMAX;
-      if (rr < rn && jj < w) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) s_k[d][rr][jj] = kv[d][q];
-      }
+    // the staged sources' precomputed kernel rows: 3 * WMAX contiguous reals per source
+    for (int e = tid; e < rn * 3 * WMAX; e += T3_TILE * T3_TILE) {
+      const int rr = e / (3 * WMAX), rem = e - rr * 3 * WMAX, d = rem / WMAX, jj = rem - d * WMAX;
+      s_k[d][rr][jj] = a.rows[(int64_t)s_src[rr] * 3 * WMAX + rem];
     }
     __syncthreads();
     // rotate the z rows onto the grid cells so that the inner loop is unconditional
