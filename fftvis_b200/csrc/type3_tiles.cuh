@@ -26,7 +26,7 @@ namespace fv {
 
 constexpr int T3_TILE = 16;     // columns per tile side (256 threads = one column each)
 constexpr int T3_NZMAX = 32;    // z cells a thread can hold in registers
-constexpr int T3_RS = 32;       // sources staged per round
+constexpr int T3_RS = 64;       // sources staged per round (each round has one phase of dependent loads: list -> source -> record rows)
 
 template <typename T>
 struct T3Geom {
@@ -149,16 +149,30 @@ t3_col_spread_kernel(T3SpreadArgs<T> a) {
   const int l0 = a.offsets[tile], l1 = a.offsets[tile + 1];
   const C* Wp = a.W + (int64_t)bpi * a.n_cap;
   const BatchParams bpar = a.bp[b];
+  // the per-source scalars of a round (list entry -> first cells, strength, coordinates) are fetched one round
+  // ahead into registers, so that this chain of dependent global loads runs under the previous round's z loops
+  int p_s = -1, p_c[3] = {0, 0, 0};
+  C p_w = make_c<T>(T(0), T(0));
+  T p_x[3] = {T(0), T(0), T(0)};
+  auto prefetch = [&](int r0) {
+    p_s = -1;
+    if (tid < T3_RS && r0 + tid < l1) {
+      p_s = a.list[r0 + tid];
+      p_c[0] = a.cells[3 * p_s]; p_c[1] = a.cells[3 * p_s + 1]; p_c[2] = a.cells[3 * p_s + 2];
+      p_w = Wp[p_s];
+      if (a.prephase) { p_x[0] = a.g.x[p_s]; p_x[1] = a.g.y[p_s]; p_x[2] = a.g.z[p_s]; }
+    }
+  };
+  prefetch(l0);
   for (int r0 = l0; r0 < l1; r0 += T3_RS) {
     const int rn = min(T3_RS, l1 - r0);
     if (tid < rn) {
-      const int s = a.list[r0 + tid];
-      s_src[tid] = s;
-      s_ix[tid] = a.cells[3 * s]; s_iy[tid] = a.cells[3 * s + 1]; s_iz[tid] = a.cells[3 * s + 2];
-      C cw = Wp[s];
+      s_src[tid] = p_s;
+      s_ix[tid] = p_c[0]; s_iy[tid] = p_c[1]; s_iz[tid] = p_c[2];
+      C cw = p_w;
       if (a.prephase) {
         double sn, cs;
-        sincos(bpar.D[0] * (double)a.g.x[s] + bpar.D[1] * (double)a.g.y[s] + bpar.D[2] * (double)a.g.z[s], &sn, &cs);
+        sincos(bpar.D[0] * (double)p_x[0] + bpar.D[1] * (double)p_x[1] + bpar.D[2] * (double)p_x[2], &sn, &cs);
         cw = cmul(cw, make_c<T>((T)cs, (T)sn));
       }
       s_w[tid] = cw;
@@ -177,6 +191,7 @@ t3_col_spread_kernel(T3SpreadArgs<T> a) {
       s_kzr[rr][z] = (z < nf2 && jz < w) ? s_k[2][rr][jz] : T(0);
     }
     __syncthreads();
+    prefetch(r0 + T3_RS);
     for (int r = 0; r < rn; ++r) {
       int jx = gx - s_ix[r]; if (jx < 0) jx += nf0;
       int jy = gy - s_iy[r]; if (jy < 0) jy += nf1;
