@@ -283,7 +283,9 @@ static int nufft3_impl(fv_plan* P, int prec, int dim, const void* x, const void*
       ta.offsets = bin_offsets; ta.list = bin_list; ta.rows = t3_rows; ta.cells = t3_cells; ta.grid = (C*)P->grid;
       StageScope ts(P, FV_STAGE_SPREAD);
       dim3 tg(ntiles, sub * ntr);
-      FV_DISPATCH_W(w, (t3_col_spread_kernel<T, WT><<<tg, T3_TILE * T3_TILE, 0, P->stream>>>(ta)));
+      const size_t ssm = t3_spread_smem<T>((w == 7 || w == 9 || w == 11 || w == 13 || w == 14) ? w : kMaxW);
+      FV_DISPATCH_W(w, (cudaFuncSetAttribute(t3_col_spread_kernel<T, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm),
+                        t3_col_spread_kernel<T, WT><<<tg, T3_TILE * T3_TILE, ssm, P->stream>>>(ta)));
       FV_LAUNCH_CHECK();
     } else {
       StageScope ts(P, FV_STAGE_ZERO);

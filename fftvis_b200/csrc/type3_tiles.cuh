@@ -21,6 +21,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_sort.cuh>
 #include <type_traits>
+#include <cuda_pipeline.h>
 
 namespace fv {
 
@@ -109,6 +110,13 @@ t3_records_kernel(T3Geom<T> g, T beta, T c, T halfw, T* __restrict__ rows, int32
   for (int j = 0; j < WMAX; ++j) r[j] = j < w ? es_kernel<T>(z0 + (T)j, beta, c, halfw) : T(0);
 }
 
+// dynamic shared memory of t3_col_spread_kernel
+template <typename T>
+inline size_t t3_spread_smem(int wmax) {
+  return sizeof(T) * (2 * 3 * T3_RS * (size_t)wmax + (size_t)T3_RS * T3_NZMAX) + sizeof(cplx_t<T>) * 2 * T3_RS +
+         sizeof(int) * 2 * 3 * T3_RS;
+}
+
 template <typename T>
 struct T3SpreadArgs {
   T3Geom<T> g;
@@ -130,10 +138,14 @@ t3_col_spread_kernel(T3SpreadArgs<T> a) {
   using C = cplx_t<T>;
   const int w = WT > 0 ? WT : a.g.w;
   constexpr int WMAX = WT > 0 ? WT : kMaxW;
-  __shared__ int s_ix[T3_RS], s_iy[T3_RS], s_iz[T3_RS], s_src[T3_RS];
-  __shared__ T s_k[3][T3_RS][WMAX];     // kernel rows of the staged sources (x, y, z)
-  __shared__ __align__(16) T s_kzr[T3_RS][T3_NZMAX];   // z row rotated onto the grid: value for cell z, 0 outside
-  __shared__ C s_w[T3_RS];
+  // two slots of staged sources: kernel rows (x, y, z), first cells, strengths; slot (i + 1) & 1 fills -- the rows by
+  // asynchronous copies (LDGSTS) -- while the z loops of round i run on slot i & 1
+  extern __shared__ __align__(16) unsigned char t3s_smem[];
+  T (*s_k)[3][T3_RS][WMAX] = reinterpret_cast<T (*)[3][T3_RS][WMAX]>(t3s_smem);                 // [2]
+  T (*s_kzr)[T3_NZMAX] = reinterpret_cast<T (*)[T3_NZMAX]>(t3s_smem + sizeof(T) * 2 * 3 * T3_RS * WMAX);   // [T3_RS]: z row
+                                                      // rotated onto the grid: value for cell z, 0 outside
+  C (*s_w)[T3_RS] = reinterpret_cast<C (*)[T3_RS]>(reinterpret_cast<unsigned char*>(s_kzr) + sizeof(T) * T3_RS * T3_NZMAX);
+  int (*s_i)[3][T3_RS] = reinterpret_cast<int (*)[3][T3_RS]>(reinterpret_cast<unsigned char*>(s_w) + sizeof(C) * 2 * T3_RS);
   const int tid = threadIdx.x;
   const int tile = blockIdx.x, ty = tile / a.g.ntx, tx = tile - ty * a.g.ntx;
   const int bpi = blockIdx.y, b = bpi / a.ntr;
@@ -149,8 +161,9 @@ t3_col_spread_kernel(T3SpreadArgs<T> a) {
   const int l0 = a.offsets[tile], l1 = a.offsets[tile + 1];
   const C* Wp = a.W + (int64_t)bpi * a.n_cap;
   const BatchParams bpar = a.bp[b];
-  // the per-source scalars of a round (list entry -> first cells, strength, coordinates) are fetched one round
-  // ahead into registers, so that this chain of dependent global loads runs under the previous round's z loops
+  // The per-source scalars of a round (list entry -> first cells, strength, coordinates) are fetched into registers
+  // one round before they are staged, and staged one round before they are used: the chain of dependent global
+  // loads list -> source -> {cells, strength, rows} runs under the z loops of the two rounds before.
   int p_s = -1, p_c[3] = {0, 0, 0};
   C p_w = make_c<T>(T(0), T(0));
   T p_x[3] = {T(0), T(0), T(0)};
@@ -163,41 +176,48 @@ t3_col_spread_kernel(T3SpreadArgs<T> a) {
       if (a.prephase) { p_x[0] = a.g.x[p_s]; p_x[1] = a.g.y[p_s]; p_x[2] = a.g.z[p_s]; }
     }
   };
-  prefetch(l0);
-  for (int r0 = l0; r0 < l1; r0 += T3_RS) {
-    const int rn = min(T3_RS, l1 - r0);
-    if (tid < rn) {
-      s_src[tid] = p_s;
-      s_ix[tid] = p_c[0]; s_iy[tid] = p_c[1]; s_iz[tid] = p_c[2];
+  // stage the prefetched round into `slot`: scalars by plain stores, this thread's source's rows by async copies
+  auto stage = [&](int slot) {
+    if (p_s >= 0) {
+      s_i[slot][0][tid] = p_c[0]; s_i[slot][1][tid] = p_c[1]; s_i[slot][2][tid] = p_c[2];
       C cw = p_w;
       if (a.prephase) {
         double sn, cs;
         sincos(bpar.D[0] * (double)p_x[0] + bpar.D[1] * (double)p_x[1] + bpar.D[2] * (double)p_x[2], &sn, &cs);
         cw = cmul(cw, make_c<T>((T)cs, (T)sn));
       }
-      s_w[tid] = cw;
+      s_w[slot][tid] = cw;
+      const T* src = a.rows + (int64_t)p_s * 3 * WMAX;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int j = 0; j < WMAX; ++j) __pipeline_memcpy_async(&s_k[slot][d][tid][j], src + d * WMAX + j, sizeof(T));
     }
-    __syncthreads();
-    // the staged sources' precomputed kernel rows: 3 * WMAX contiguous reals per source
-    for (int e = tid; e < rn * 3 * WMAX; e += T3_TILE * T3_TILE) {
-      const int rr = e / (3 * WMAX), rem = e - rr * 3 * WMAX, d = rem / WMAX, jj = rem - d * WMAX;
-      s_k[d][rr][jj] = a.rows[(int64_t)s_src[rr] * 3 * WMAX + rem];
-    }
-    __syncthreads();
+    __pipeline_commit();
+  };
+  prefetch(l0);
+  stage(0);
+  prefetch(l0 + T3_RS);
+  int slot = 0;
+  for (int r0 = l0; r0 < l1; r0 += T3_RS, slot ^= 1) {
+    const int rn = min(T3_RS, l1 - r0);
+    __pipeline_wait_prior(0);
+    __syncthreads();                                       // slot's rows and scalars are in; the other slot is free
     // rotate the z rows onto the grid cells so that the inner loop is unconditional
     for (int e = tid; e < rn * T3_NZMAX; e += T3_TILE * T3_TILE) {
       const int rr = e / T3_NZMAX, z = e - rr * T3_NZMAX;
-      int jz = z - s_iz[rr]; if (jz < 0) jz += nf2;
-      s_kzr[rr][z] = (z < nf2 && jz < w) ? s_k[2][rr][jz] : T(0);
+      int jz = z - s_i[slot][2][rr]; if (jz < 0) jz += nf2;
+      s_kzr[rr][z] = (z < nf2 && jz < w) ? s_k[slot][2][rr][jz] : T(0);
     }
+    stage(slot ^ 1);                                       // the round after this one (in registers since the last round)
+    prefetch(r0 + 2 * T3_RS);                              // and the one after that
     __syncthreads();
-    prefetch(r0 + T3_RS);
     for (int r = 0; r < rn; ++r) {
-      int jx = gx - s_ix[r]; if (jx < 0) jx += nf0;
-      int jy = gy - s_iy[r]; if (jy < 0) jy += nf1;
+      int jx = gx - s_i[slot][0][r]; if (jx < 0) jx += nf0;
+      int jy = gy - s_i[slot][1][r]; if (jy < 0) jy += nf1;
       if (owner && jx < w && jy < w) {
-        const T kxy = s_k[0][r][jx] * s_k[1][r][jy];
-        const C cw = s_w[r];
+        const T kxy = s_k[slot][0][r][jx] * s_k[slot][1][r][jy];
+        const C cw = s_w[slot][r];
         const T cr = cw.x * kxy, ci = cw.y * kxy;
         // two z cells per shared-memory load (the row is 16-byte aligned and read as a broadcast)
         using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
@@ -210,7 +230,7 @@ t3_col_spread_kernel(T3SpreadArgs<T> a) {
         }
       }
     }
-    __syncthreads();
+    __syncthreads();                                       // s_kzr is rewritten by the next round
   }
   if (owner) {
     C* gp = a.grid + (int64_t)bpi * nf2 * nf1 * nf0 + (int64_t)gy * nf0 + gx;
