@@ -220,7 +220,7 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   g.Tbuf = (const C*)P->tbuf; g.nf = (int)nf; g.pitch = pitch; g.ncols = ncols; g.cols_per_cta = cpc; g.ntr = ntr;
   g.tw = (const C*)F->tw; g.st = F->st; g.col_off = tab->col_off; g.s_k = tab->s_k; g.s_pos = tab->s_pos;
   g.s_scale = (const T*)(use_xd ? tab->s_scale_y : tab->s_scale); g.epi = make_epi(epi);
-  g.t_rowmajor = use_xd ? 1 : 0;
+  g.t_blocked = use_xd ? 1 : 0;
   // blocked T (x-direct pass 1): one CTA per block of 8 columns, transformed in the block's own layout
   const size_t smem8 = sizeof(float2) * (size_t)nf * 9 + 16;  // the block + twiddles (<= nf entries, rounded up to 16 bytes)
   if (use_xd && P->t1_cols == 0 && smem8 <= 74 * 1024) {

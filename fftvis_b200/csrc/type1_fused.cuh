@@ -702,8 +702,8 @@ t1_spread_fftx_kernel(T1SpreadArgs<T> a) {
 
 template <typename T>
 struct T1GatherArgs {
-  const cplx_t<T>* Tbuf;         // (nb, ntr, ncols, nf); (nb, ntr, ceil(ncols / 8), nf, 8) when t_rowmajor (x-direct pass 1)
-  int nf, pitch, ncols, cols_per_cta, ntr, t_rowmajor;
+  const cplx_t<T>* Tbuf;         // (nb, ntr, ncols, nf); (nb, ntr, ceil(ncols / 8), nf, 8) when t_blocked (x-direct pass 1)
+  int nf, pitch, ncols, cols_per_cta, ntr, t_blocked;
   const cplx_t<T>* tw;
   FftStages st;
   const int32_t* col_off;        // (ncols + 1) ranges into the column-sorted baseline tables
@@ -728,7 +728,7 @@ t1_ffty_gather_kernel(T1GatherArgs<T> a) {
   const C* Tb = a.Tbuf + ((int64_t)bpi * a.ncols + c0) * nf;
   // columns -> shared memory with asynchronous copies (LDGSTS): every element's load is in flight
   // at once instead of a register round trip per element
-  if (a.t_rowmajor) {
+  if (a.t_blocked) {
     // x-direct pass 1 writes T in blocks of 8 columns: [column group][row][8 columns], so a CTA's columns are whole
     // contiguous blocks of nf x 8 entries.  16-byte loads (two columns of one row), five in flight per thread,
     // then one 8-byte shared-memory store per column: the transpose to column vectors happens on the way in.
