@@ -366,6 +366,11 @@ class GPUSimulationEngine(SimulationEngine):
             ncols = max((pt.ncols for pt in pairs), default=None) if is_gridded else None
             npairs = nbeam * (nbeam + 1) // 2 if (beam_coefs is not None and nbeam <= 5) else 1
             fb = self._auto_batch(is_gridded, n_modes, P * npairs, precision, eps, float(upsample_factor), n_cap, ncols)
+            # equal batches: a short last batch (a rank's 128 frequencies as 54 + 54 + 20) leaves the streams that
+            # run consecutive batches side by side unevenly loaded
+            nfl = max(1, f_hi - f_lo)
+            if nfl > fb:
+                fb = -(-nfl // -(-nfl // fb))
         return SimulationPlan(
             precision=precision, polarized=polarized, polarized_sky=pol_sky, nfeeds=2 if polarized else 1,
             eps=float(eps), upsample_factor=float(upsample_factor), use_type1=is_gridded,
