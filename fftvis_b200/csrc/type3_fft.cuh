@@ -105,22 +105,28 @@ t3_fft_contig_kernel(T3FftArgs<T> a) {
   for (int i = threadIdx.x; i < a.st.tw_len; i += blockDim.x) tw[i] = a.tw[i];
   for (int i = threadIdx.x; i < nv * pitch; i += blockDim.x) vecs[i] = make_c<T>(T(0), T(0));
   __syncthreads();
-  for (int i = threadIdx.x; i < nv * nin; i += blockDim.x) {
-    const int v = i / nin, k = i - v * nin;
+  // one vector after the other: the (s3, s2) row of a vector and its deconvolution factors are found once per
+  // vector, not by 64-bit divisions per element
+  for (int v = 0; v < nv; ++v) {
     const int64_t vg = v0 + v;
     const int s3 = (int)(vg / a.nf2), s2 = (int)(vg - (int64_t)s3 * a.nf2);
-    T sc = a.inv1[k] * a.inv2[s2];
-    if (a.inv3) sc *= a.inv3[s3];
-    C x = in[i];
-    x.x *= sc; x.y *= sc;
-    vecs[v * pitch + t3_mode_slot(k, nin, n)] = x;
+    const T sc23 = a.inv3 ? a.inv2[s2] * a.inv3[s3] : a.inv2[s2];
+    const C* iv = in + (int64_t)v * nin;
+    C* dv = vecs + v * pitch;
+    for (int k = threadIdx.x; k < nin; k += blockDim.x) {
+      const T sc = a.inv1[k] * sc23;
+      C x = iv[k];
+      x.x *= sc; x.y *= sc;
+      dv[t3_mode_slot(k, nin, n)] = x;
+    }
   }
   __syncthreads();
   smem_fft_cta<T>(vecs, nv, pitch, n, tw, a.st);
   C* out = a.out + (int64_t)q * a.out_q + v0 * n;
-  for (int i = threadIdx.x; i < nv * n; i += blockDim.x) {
-    const int v = i / n, j = i - v * n;
-    out[i] = vecs[v * pitch + a.pos[j]];
+  for (int v = 0; v < nv; ++v) {
+    const C* sv = vecs + v * pitch;
+    C* ov = out + (int64_t)v * n;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) ov[j] = sv[a.pos[j]];
   }
 }
 
