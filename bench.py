@@ -469,10 +469,15 @@ def run_gpu(args):
                                         "streams and times only the dominant stage, for the roofline)"}
         if roof is not None and plan2.use_type1 and stages_all.get("spread", (0, 0))[1]:
             sp_ms1, sp_n1 = stages_all["spread"]
+            roof["step_level"] = {
+                "achieved": roof["alg_bytes_per_launch"] * roof["launches"] / (ms * 1e-3) / 1e9,
+                "frac": roof["alg_bytes_per_launch"] * roof["launches"] / (ms * 1e-3) / 1e9 / roof["peak"],
+                "note": "all of this kernel's algorithmic bytes over the WHOLE timed region's wall time (every other "
+                        "kernel's time included): the sustained figure when launches of several streams overlap"}
             roof["alone"] = {"avg_launch_ms": sp_ms1 / sp_n1,
                              "frac": roof["alg_bytes_per_launch"] / (sp_ms1 / sp_n1 * 1e-3) / 1e9 / roof["peak"],
                              "note": "the same kernel timed in the single-stream extra step (no co-running kernels); "
-                                     "`achieved` / `frac` above are from the timed region, where the launches of two "
+                                     "`achieved` / `frac` above are from the timed region, where the launches of several "
                                      "streams overlap and each launch therefore lasts longer"}
         cpu = None
         if world == 1 and not args.no_cpu:
