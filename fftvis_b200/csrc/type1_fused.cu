@@ -133,7 +133,8 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
   if (fixed1 + np * row_bytes * R > smem_max) { set_error("fine-grid row does not fit shared memory: use the cuFFT type-1 path"); return FV_ERR_UNSUPPORTED; }
   // x-direct pass 1 (type1_xdirect.cuh): single precision, a grid of several strips
   const bool use_xd = sizeof(T) == 4 && P->t1_xdirect && !whole && P->t1_rows == 0 && t1_xdirect_built(w) &&
-                      nf >= 2 * (t1_xdirect_rows() + w);
+                      nf >= 2 * (t1_xdirect_rows() + w) &&
+                      ceil_div(nf, t1_xdirect_rows()) <= 1024;   // per-warp strip counters of the prep pass in shared memory
   if (use_xd) R = t1_xdirect_rows();
   // fold every (frequency, source) point once
   const size_t per = (size_t)nb * n_cap;
