@@ -157,6 +157,10 @@ def shard_inputs(kw: dict, lo: int, hi: int) -> dict:
 _CPU_ONLY = ("nprocesses", "nthreads", "force_use_ray", "trace_mem", "enable_memory_monitor")
 
 
+SHARED_HOST_MAX_BYTES = int(__import__("os").environ.get("FV_SHARED_HOST_MAX_BYTES", 16 << 30))
+_NO_SHARED = object()
+
+
 def _simulate_shared(engine, plan, shards, nfreqs: int, group, root: int):
     """``host_result="shared"``: this rank's block of the result streamed into the shared host array."""
     from .gpu_simulate import _CDT, _NP_C
@@ -169,6 +173,8 @@ def _simulate_shared(engine, plan, shards, nfreqs: int, group, root: int):
     st = engine.__dict__.setdefault("_shared_state", {"slot": 0})
     st["slot"] ^= 1
     seg = SharedHostResult.get(nbytes, group, root, st["slot"])
+    if not seg.ok:
+        return _NO_SHARED
     full = seg.array(shape, cdt)
     mine = torch.from_numpy(full[lo:hi])                       # contiguous: the frequency axis is the outermost
     if hi > lo:
@@ -255,14 +261,20 @@ class SharedHostResult:
         from multiprocessing import shared_memory
         rank = dist.get_rank(group)
         name = [None]
+        self.shm = None
         if rank == root:
-            self.shm = shared_memory.SharedMemory(create=True, size=max(int(nbytes), 1))
-            name[0] = self.shm.name
+            try:
+                self.shm = shared_memory.SharedMemory(create=True, size=max(int(nbytes), 1))
+                name[0] = self.shm.name
+            except Exception:                 # /dev/shm too small, no permission ...: every rank learns it below
+                self.shm = None
         dist.broadcast_object_list(name, src=dist.get_global_rank(group, root) if group is not None else root,
                                    group=group)
+        self.ok = name[0] is not None
+        if not self.ok:
+            return
         if rank != root:
             self.shm = shared_memory.SharedMemory(name=name[0])
-        if rank != root:
             try:                              # attaching registered the segment with this process' resource tracker,
                 from multiprocessing import resource_tracker      # which would unlink it again at exit
                 resource_tracker.unregister(self.shm._name, "shared_memory")
@@ -273,8 +285,16 @@ class SharedHostResult:
         self.bytes_view = np.ndarray((self.nbytes,), dtype=np.uint8, buffer=self.shm.buf)
         self.registered = False
         if torch.cuda.is_available() and self.nbytes:
-            rc = torch.cuda.cudart().cudaHostRegister(self.bytes_view.ctypes.data, self.nbytes, 0)
+            rt = torch.cuda.cudart()
+            rc = rt.cudaHostRegister(self.bytes_view.ctypes.data, self.nbytes, 0)
             self.registered = int(rc) == 0
+            if not self.registered:
+                # locked-memory limit, unsupported mapping ...: clear the error so that it does not surface at the next
+                # CUDA call; the caller then copies its block once at the end instead of streaming slabs
+                try:
+                    rt.cudaGetLastError()
+                except Exception:
+                    pass
         dist.barrier(group)
         if rank == root:
             self.shm.unlink()                 # the mappings keep it alive; nothing is left behind in /dev/shm
@@ -324,7 +344,14 @@ def simulate_vis_sharded(engine, *, group=None, dst: int | None = 0, shards=None
     plan = engine.prepare(**kw)
     P = 4 if plan.polarized else 1
     if host_result == "shared" and dst is not None:
-        return _simulate_shared(engine, plan, shards, nfreqs, group, root)
+        # beyond SHARED_HOST_MAX_BYTES (page-locking tens of GB of shared memory is refused on common settings), or
+        # where the segment cannot be created, the call goes through the NCCL gather instead -- the same decision on
+        # every rank
+        nbytes = nfreqs * plan.ntimes * P * plan.nbls * (8 * plan.precision)
+        if nbytes <= SHARED_HOST_MAX_BYTES:
+            res = _simulate_shared(engine, plan, shards, nfreqs, group, root)
+            if res is not _NO_SHARED:
+                return res
     host = None
     if rank == root:
         from .gpu_simulate import _CDT

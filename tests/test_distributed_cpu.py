@@ -131,6 +131,21 @@ def _shared_worker(rank, world, port, q):
                     ok &= bool(np.all(full[a:b].real == (r + 1) * (slot + 1)))
                     ok &= bool(np.all(full[a:b].imag == np.arange(a, b)[:, None, None, None]))
             dist.barrier()
+        # a segment that cannot be created (here: every rank's constructor raises) is reported as not ok on EVERY
+        # rank, so that all of them fall back to the gather together
+        from multiprocessing import shared_memory
+
+        class Boom:
+            def __init__(self, *a, **k):
+                raise OSError("no space left on /dev/shm")
+
+        real = shared_memory.SharedMemory
+        shared_memory.SharedMemory = Boom
+        try:
+            seg = SharedHostResult.get(12345, None, 0, 7)
+        finally:
+            shared_memory.SharedMemory = real
+        ok &= seg.ok is False
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
