@@ -264,6 +264,12 @@ class SharedHostResult:
         self.shm = None
         if rank == root:
             try:
+                # tmpfs lets a segment be created larger than the space it has and faults (SIGBUS) on the first write
+                # beyond it: ask for the room first
+                import os
+                vfs = os.statvfs("/dev/shm")
+                if vfs.f_bavail * vfs.f_frsize < int(nbytes) + (64 << 20):
+                    raise OSError("not enough room in /dev/shm")
                 self.shm = shared_memory.SharedMemory(create=True, size=max(int(nbytes), 1))
                 name[0] = self.shm.name
             except Exception:                 # /dev/shm too small, no permission ...: every rank learns it below
