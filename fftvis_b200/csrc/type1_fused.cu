@@ -165,9 +165,6 @@ static int nufft2d1_fused_impl(fv_plan* P, int prec, const void* bx, const void*
                        4 * 2 * (8 * 32 * sizeof(T) + 8 * sizeof(C)) + 256 <= smem_max;
   }
   const bool use_small = small_ok && (P->t1_small == 2 || (P->t1_small == 1 && n_cap >= 4096));
-  if (ntr > 4 && !use_small) {
-    // the strip kernel takes any transform count as well; nothing to do
-  }
   if (use_xd) {
     rc = t1_xdirect_pass1_entry(P, bx, by, n_dev, n_cap, nb, ntr, W, nf, w, beta, tab);
     if (rc) return rc;
