@@ -335,3 +335,54 @@ def cpu_nufft3d(x, y, z, weights, u, v, w, eps, upsample_factor=2, n_threads=Non
 def cpu_nufft2d_type1(x, y, weights, n_modes, index, eps, upsample_factor=2, n_threads=None):
     model = nufft2d1(x, y, weights, n_modes, eps, +1, float(upsample_factor), n_threads)
     return model[..., index[0], index[1]]
+
+
+# --------------------------------------------------------------------------------------
+# restatements of the product's two algebraic shortcuts (checked on the CPU against the direct sum / numpy FFT)
+# --------------------------------------------------------------------------------------
+def nufft2d1_xdirect(x, y, c, m1, m2, eps, upsampfac=2.0):
+    """Type-1 values at the integer modes (m1[k], m2[k]) by the hybrid the product's single-precision pass 1 uses
+    (csrc/type1_xdirect.cuh): an exact Fourier sum along x over the distinct first mode numbers, the
+    exponential-of-semicircle kernel + FFT + deconvolution along y only:
+
+        T[col, row] = sum_j c_j phi((row - gy_j)) exp(+i k_col x_j);   V[k] = FFT_y(T[col(k)])[m2[k]] / phihat(m2[k])
+
+    Plain numpy in fp64 (test infrastructure: small sizes)."""
+    x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+    c2 = np.atleast_2d(np.asarray(c, np.complex128))
+    m1, m2 = np.asarray(m1), np.asarray(m2)
+    ns, beta = kernel_params(eps, upsampfac, 2)
+    n_modes = 2 * int(max(np.abs(m1).max(), np.abs(m2).max())) + 1
+    nf = type1_grid_size(n_modes, ns, upsampfac)
+    cols, col_of = np.unique(m1, return_inverse=True)
+    # fold y onto the grid: y = -pi -> 0, 0 -> nf / 2 (the half-grid shift is inside kernel_ft_series' sign)
+    gy = ((y / (2 * np.pi) + 0.5) % 1.0) * nf
+    i0 = np.ceil(gy - ns / 2.0).astype(int)
+    T = np.zeros((c2.shape[0], cols.size, nf), np.complex128)
+    phase = np.exp(1j * np.outer(cols, x))                                  # (ncols, n): exact along x
+    for j in range(ns):
+        ker = es_kernel(i0 + j - gy, ns, beta)                               # (n,)
+        rows = (i0 + j) % nf
+        for t in range(c2.shape[0]):
+            np.add.at(T[t], (slice(None), rows), phase * (c2[t] * ker)[None, :])
+    Fy = sfft.ifft(T, axis=2, norm="forward")                               # e^{+i ...} along y
+    ph = kernel_ft_series(nf, ns, beta)
+    out = Fy[:, col_of, m2 % nf] / ph[np.abs(m2)][None, :]
+    return out[0] if np.ndim(c) == 1 else out
+
+
+def padded_fft_half_length(data):
+    """The zero-padded, centred-mode transform of the type-3 inner FFT in the half-length form of
+    csrc/type3_fft.cuh: ``data`` holds the nin (even) centred modes k - nin / 2; the result is the n = 2 nin point
+    transform X[k] = sum_m data[m] exp(+2 pi i (m - nin / 2) k / n), from two nin-point transforms."""
+    y = np.asarray(data, np.complex128)
+    nin = y.shape[-1]
+    n = 2 * nin
+    j = np.arange(nin)
+    even = sfft.ifft(y, axis=-1, norm="forward")
+    odd = sfft.ifft(y * np.exp(2j * np.pi * j / n), axis=-1, norm="forward")
+    sgn = np.where(j % 2 == 0, 1.0, -1.0)
+    out = np.empty(y.shape[:-1] + (n,), np.complex128)
+    out[..., 0::2] = sgn * even
+    out[..., 1::2] = sgn * (-1j) * odd
+    return out

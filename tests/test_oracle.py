@@ -87,3 +87,40 @@ def test_spread_thread_invariance():
     b = nc.spread(pts, c, (40, 64), 7, 2.3 * 7, nthreads=4)
     np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-14)
     assert a.shape == (1, 64, 40)
+
+
+@pytest.mark.parametrize("eps", [1e-12, 1e-6, 1e-3])
+def test_xdirect_hybrid_restatement_matches_direct_sum(eps):
+    """The algebra of the product's x-direct pass 1 (exact Fourier sum along x, kernel + FFT + deconvolution along
+    y only) restated in numpy: never worse than the two-dimensional transform's tolerance."""
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(11)
+    n, nk, N = 400, 60, 41
+    x, y = rng.uniform(-30, 30, n), rng.uniform(-30, 30, n)
+    x[:4] = [np.pi, -np.pi, 3 * np.pi - 1e-3, 1e-3 - np.pi]                 # footprints across the periodic edge in y too
+    y[2:6] = [np.pi - 1e-3, -np.pi, 5 * np.pi, -3 * np.pi + 2e-3]
+    c = rng.normal(size=(2, n)) + 1j * rng.normal(size=(2, n))
+    idx = rng.integers(-(N // 2), N // 2 + 1, size=(2, nk))
+    idx[:, :3] = [[-(N // 2), N // 2, 0], [N // 2, -(N // 2), 0]]
+    got = nc.nufft2d1_xdirect(x, y, c, idx[0], idx[1], eps)
+    want = nc.direct_sum(x, y, None, c, idx[0], idx[1], None)
+    full = nc.cpu_nufft2d_type1(x, y, c, N, idx, eps)
+    err = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert err < 10 * eps
+    assert err <= 1.5 * np.linalg.norm(full - want) / np.linalg.norm(want) + 1e-14
+
+
+def test_half_length_form_of_the_padded_fft():
+    """X[2k] = (-1)^k FFT_nin(y)[k], X[2k+1] = (-1)^k (-i) FFT_nin(y_j e^{2 pi i j / n})[k] (csrc/type3_fft.cuh) against
+    numpy's transform of the explicitly padded vector."""
+    from oracle import nufft_cpu as nc
+    rng = np.random.default_rng(3)
+    for nin in (30, 36, 1620):
+        data = rng.normal(size=(3, nin)) + 1j * rng.normal(size=(3, nin))
+        n = 2 * nin
+        padded = np.zeros((3, n), complex)
+        m = np.arange(nin) - nin // 2
+        padded[:, m % n] = data
+        want = np.fft.ifft(padded, axis=-1) * n                              # sum_j x_j e^{+2 pi i j k / n}
+        got = nc.padded_fft_half_length(data)
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13
